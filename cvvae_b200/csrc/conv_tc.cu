@@ -1,0 +1,536 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), operands
+// staged by TMA straight from the channels-last activation tensor: no im2col buffer ever exists.
+//
+// GEMM view: M = output positions, N = Cout, K = taps x Cin.  One CTA owns an output patch of
+// TH x TW positions of one output frame (TH = NACC * 128/TW) and N_cta output channels; it keeps NACC
+// accumulators of 128 x N_cta fp32 in TMEM (<= 512 columns) so that every weight tile staged in shared
+// memory feeds NACC MMAs, and every activation slab feeds all KH row-taps:
+//
+//   A slab  (one per kt, kw, 64-channel block): the (TH+KH-1) x TW input window, shifted by kw, loaded by
+//           ONE 5-D TMA box into a SWIZZLE_128B buffer [row][w][64 ch].  Because the slab pitch is exactly
+//           TW positions (a multiple of 8 -> 1024 B), the A operand of row-tap kh / sub-tile s is the same
+//           buffer at byte offset ((s*ROWS + kh) * TW) * 128: a 1024-B aligned UMMA descriptor, no copy.
+//           Zero padding in H/W is TMA out-of-bounds fill; time padding is a coordinate clamp (replicate)
+//           or a skipped tap (zeros).  Strided (down-sampling) convs use TMA element strides.
+//   B tile  (one per tap, 64-channel block): [N_cta][64] slice of the packed weights [tap][Cout][Cin].
+//
+// Warp roles (256 threads): w0 A-producer, w1 B-producer, w2 MMA issuer (one elected thread), w3 TMEM
+// allocator, w4-7 epilogue (TMEM -> registers -> bias/alpha/residual -> 16-bit stores, with the
+// time-interleave scatter of Upsample3D folded into the store address).
+//
+// Replaces cuDNN behind CausalConv3d / nn.Conv3d / Conv2dWithExtraDim / Downsample3D / Upsample3D
+// (reference: models/vae_models.py:198-340, models/vae_blocks3d_sd3.py:16-364); see include/cvvae_b200.h.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cvvae {
+
+struct ConvTcParams {
+  int B, T_in, T_out, H_out, W_out, Cin, Cout;
+  int KT, KH, KW, st, sh, sw, off_t, off_h, off_w, pad_t;
+  int up_time, flags;
+  float alpha;
+  // tiling
+  int TW, ROWS, NACC, TH, N_cta, KHs, n_hgroups, slab_rows;
+  int tiles_w, tiles_h, n_tiles_n, cblocks, flat;
+  int NA, NB;
+  uint32_t slab_bytes, b_bytes, idesc;
+  // epilogue
+  const float* bias;
+  const void* residual;
+  void* y;
+  long long ys_b, ys_t, ys_h, ys_w, ys_c;
+  int yC, yT, vec_ok;
+};
+
+static constexpr int kThreads = 256;
+static constexpr uint32_t kTmemCols = 512;
+
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) { ptx::mbar_wait(bar, parity); }
+
+struct TileCoord {
+  int b, t, h0, w0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p) {
+  int id = blockIdx.x;
+  TileCoord c;
+  c.n0 = (id % p.n_tiles_n) * p.N_cta;
+  id /= p.n_tiles_n;
+  c.t = id % p.T_out;
+  id /= p.T_out;
+  c.w0 = (id % p.tiles_w) * (p.flat ? p.NACC * 128 : p.TW);
+  id /= p.tiles_w;
+  c.h0 = (id % p.tiles_h) * p.TH;
+  c.b = id / p.tiles_h;
+  return c;
+}
+
+// Enumerate the activation-slab steps of one tile in the order every role agrees on.
+// f(kt, ti, hg, kw, cb)
+template <class F>
+__device__ __forceinline__ void for_each_slab(const ConvTcParams& p, int t, F&& f) {
+  for (int kt = 0; kt < p.KT; ++kt) {
+    int ti = t * p.st + kt + p.off_t;
+    if (ti < 0 || ti >= p.T_in) {
+      if (p.pad_t == CVVAE_PAD_ZERO) continue;
+      ti = ti < 0 ? 0 : p.T_in - 1;
+    }
+    for (int hg = 0; hg < p.n_hgroups; ++hg)
+      for (int kw = 0; kw < p.KW; ++kw)
+        for (int cb = 0; cb < p.cblocks; ++cb) f(kt, ti, hg, kw, cb);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + static_cast<size_t>(p.NA) * p.slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(p.NB) * p.b_bytes);
+  uint64_t* fullA = bars;         // [8]
+  uint64_t* emptyA = bars + 8;    // [8]
+  uint64_t* fullB = bars + 16;    // [8]
+  uint64_t* emptyB = bars + 24;   // [8]
+  uint64_t* accFull = bars + 32;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const TileCoord tc = decode_tile(p);
+  // sub-tiles that contain at least one valid output position
+  int nacc_eff;
+  if (p.flat) {
+    int rem = p.W_out - tc.w0;
+    nacc_eff = min(p.NACC, (rem + 127) / 128);
+  } else {
+    int rem = p.H_out - tc.h0;
+    nacc_eff = min(p.NACC, (rem + p.ROWS - 1) / p.ROWS);
+  }
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.NA; ++i) {
+      ptx::mbar_init(&fullA[i], 1);
+      ptx::mbar_init(&emptyA[i], 1);
+    }
+    for (int i = 0; i < p.NB; ++i) {
+      ptx::mbar_init(&fullB[i], 1);
+      ptx::mbar_init(&emptyB[i], 1);
+    }
+    ptx::mbar_init(accFull, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 3) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- A producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
+        wait_bar(&emptyA[slot], phase ^ 1);
+        uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_bytes;
+        if (p.flat) {
+          ptx::mbar_expect_tx(&fullA[slot], static_cast<uint32_t>(nacc_eff) * 128u * 128u);
+          for (int s = 0; s < nacc_eff; ++s)
+            ptx::tma_load_5d(dst + s * 16384, &tmA, &fullA[slot], cb * 64, tc.w0 + s * 128, 0, ti, tc.b);
+        } else {
+          ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
+          ptx::tma_load_5d(dst, &tmA, &fullA[slot], cb * 64, tc.w0 * p.sw + kw + p.off_w,
+                           tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
+        }
+        if (++slot == p.NA) {
+          slot = 0;
+          phase ^= 1;
+        }
+      });
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- B producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
+        for (int khs = 0; khs < p.KHs; ++khs) {
+          const int tap = (kt * p.KH + hg * p.KHs + khs) * p.KW + kw;
+          wait_bar(&emptyB[slot], phase ^ 1);
+          ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+          ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
+          if (++slot == p.NB) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      });
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int slotA = 0, slotB = 0;
+      uint32_t phaseA = 0, phaseB = 0;
+      uint32_t accumulate = 0;
+      const uint32_t sub_stride = p.flat ? 16384u : static_cast<uint32_t>(p.ROWS * p.TW) * 128u;
+      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
+        wait_bar(&fullA[slotA], phaseA);
+        const uint32_t a_slot = ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes);
+        for (int khs = 0; khs < p.KHs; ++khs) {
+          wait_bar(&fullB[slotB], phaseB);
+          ptx::tc_fence_after();
+          const uint32_t b_slot = ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes);
+          const uint32_t a_tap = a_slot + static_cast<uint32_t>(khs * p.TW) * 128u;
+          for (int s = 0; s < nacc_eff; ++s) {
+            const uint32_t a_sub = a_tap + s * sub_stride;
+            const uint32_t d = tmem_base + static_cast<uint32_t>(s * p.N_cta);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ptx::umma_f16(d, ptx::umma_desc_k_sw128(a_sub + k * 32, 1024), ptx::umma_desc_k_sw128(b_slot + k * 32, 1024),
+                            p.idesc, accumulate | static_cast<uint32_t>(k));
+            }
+          }
+          accumulate = 1;
+          ptx::umma_commit(&emptyB[slotB]);
+          if (++slotB == p.NB) {
+            slotB = 0;
+            phaseB ^= 1;
+          }
+        }
+        ptx::umma_commit(&emptyA[slotA]);
+        if (++slotA == p.NA) {
+          slotA = 0;
+          phaseA ^= 1;
+        }
+      });
+      ptx::umma_commit(accFull);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------- epilogue
+    using E = Elem<DT>;
+    const int q = warp - 4;                 // TMEM lane quarter
+    const int r = q * 32 + lane;            // accumulator row owned by this thread
+    wait_bar(accFull, 0);
+    ptx::tc_fence_after();
+    const int chalf = p.up_time == 2 ? p.Cout / 2 : p.Cout;
+    for (int s = 0; s < nacc_eff; ++s) {
+      int h, w;
+      if (p.flat) {
+        h = 0;
+        w = tc.w0 + s * 128 + r;
+      } else {
+        h = tc.h0 + s * p.ROWS + r / p.TW;
+        w = tc.w0 + r % p.TW;
+      }
+      const bool pix_ok = (h < p.H_out) && (w < p.W_out);
+      const long long m_index =
+          ((static_cast<long long>(tc.b) * p.T_out + tc.t) * p.H_out + h) * static_cast<long long>(p.W_out) + w;
+      for (int c0 = 0; c0 < p.N_cta; c0 += 32) {
+        const int cg0 = tc.n0 + c0;
+        if (cg0 >= p.Cout) break;  // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s * p.N_cta + c0), v);
+        ptx::tmem_ld_wait();
+        if (!pix_ok) continue;
+        // output coordinates (time interleave of Upsample3D folded in)
+        int n_il = 0, cbase = cg0, t_o = tc.t;
+        if (p.up_time == 2) {
+          n_il = cg0 / chalf;
+          cbase = cg0 - n_il * chalf;
+          t_o = 2 * tc.t + n_il - 1;
+          if (t_o < 0) continue;
+        }
+        const long long off = tc.b * p.ys_b + t_o * p.ys_t + h * p.ys_h + w * p.ys_w;
+        const float bias_m = (p.bias && (p.flags & CVVAE_CONV_BIAS_ALONG_M)) ? __ldg(p.bias + m_index) : 0.f;
+        const bool chunk_full = (cg0 + 32 <= p.Cout) && (p.up_time != 2 || (cbase + 32 <= chalf));
+        if (p.flags & CVVAE_CONV_OUT_F32) {
+          // fp32 logits (S = q k^T): no residual, no interleave
+          float* yf = reinterpret_cast<float*>(p.y) + off;
+          if (p.vec_ok && chunk_full) {
+            float4* y4 = reinterpret_cast<float4*>(yf + cbase * p.ys_c);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float o4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float a = __uint_as_float(v[g * 4 + j]) * p.alpha;
+                if (p.bias) a += (p.flags & CVVAE_CONV_BIAS_ALONG_M) ? bias_m : __ldg(p.bias + cg0 + g * 4 + j);
+                o4[j] = a;
+              }
+              y4[g] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            }
+          } else {
+            for (int c = 0; c < 32 && cg0 + c < p.Cout; ++c) {
+              float a = __uint_as_float(v[c]) * p.alpha;
+              if (p.bias) a += (p.flags & CVVAE_CONV_BIAS_ALONG_M) ? bias_m : __ldg(p.bias + cg0 + c);
+              yf[(cg0 + c) * p.ys_c] = a;
+            }
+          }
+        } else if (p.vec_ok && chunk_full) {
+          typename E::T* yp = reinterpret_cast<typename E::T*>(p.y) + off + cbase;
+          const typename E::T* rp =
+              p.residual ? reinterpret_cast<const typename E::T*>(p.residual) + off + cbase : nullptr;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 rv = make_uint4(0, 0, 0, 0);
+            if (rp) rv = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = g * 8 + j * 2;
+              float a0 = __uint_as_float(v[c]) * p.alpha;
+              float a1 = __uint_as_float(v[c + 1]) * p.alpha;
+              if (p.bias) {
+                if (p.flags & CVVAE_CONV_BIAS_ALONG_M) {
+                  a0 += bias_m;
+                  a1 += bias_m;
+                } else {
+                  a0 += __ldg(p.bias + cg0 + c);
+                  a1 += __ldg(p.bias + cg0 + c + 1);
+                }
+              }
+              if (rp) {
+                float2 rf = E::to_f2(rw[j]);
+                a0 += rf.x;
+                a1 += rf.y;
+              }
+              ow[j] = E::pack2(a0, a1);
+            }
+            reinterpret_cast<uint4*>(yp)[g] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        } else {
+          for (int c = 0; c < 32; ++c) {
+            const int cg = cg0 + c;
+            if (cg >= p.Cout) break;
+            int cc = cg, tt = tc.t;
+            if (p.up_time == 2) {
+              const int n2 = cg / chalf;
+              cc = cg - n2 * chalf;
+              tt = 2 * tc.t + n2 - 1;
+              if (tt < 0) continue;
+            }
+            const long long o2 = tc.b * p.ys_b + tt * p.ys_t + h * p.ys_h + w * p.ys_w + cc * p.ys_c;
+            float a = __uint_as_float(v[c]) * p.alpha;
+            if (p.bias) a += (p.flags & CVVAE_CONV_BIAS_ALONG_M) ? bias_m : __ldg(p.bias + cg);
+            if (p.residual) a += E::to_f(reinterpret_cast<const typename E::T*>(p.residual)[o2]);
+            reinterpret_cast<typename E::T*>(p.y)[o2] = E::from_f(a);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                       const cuuint32_t* box, const cuuint32_t* estr) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return false;
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(ptr), dims, strides_b, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+              rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+    return false;
+  }
+  return true;
+}
+
+bool conv_tc_eligible(const cvvae_conv_desc* d, const char** why) {
+  const cvvae_tensor5& x = d->x;
+  auto fail = [&](const char* m) {
+    if (why) *why = m;
+    return false;
+  };
+  if (x.s_c != 1) return fail("input channel stride != 1");
+  if (d->w_ld % 8 != 0 || (d->w_ld == 0 && x.C % 8 != 0)) return fail("weight row stride not a 16-byte multiple");
+  if ((x.s_w % 8) || (x.s_h % 8) || (x.s_t % 8) || (x.s_b % 8)) return fail("input strides not 16-byte multiples");
+  if (reinterpret_cast<uintptr_t>(x.ptr) % 16) return fail("input pointer not 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(d->w) % 16) return fail("weight pointer not 16-byte aligned");
+  if (d->pad_hw != CVVAE_PAD_ZERO) {
+    // replicate padding in H/W is only needed when a tap can actually leave the image
+    const int lo_h = d->off_h, hi_h = (d->y.H - 1) * d->sh + d->KH - 1 + d->off_h;
+    const int lo_w = d->off_w, hi_w = (d->y.W - 1) * d->sw + d->KW - 1 + d->off_w;
+    if (lo_h < 0 || lo_w < 0 || hi_h >= x.H || hi_w >= x.W) return fail("replicate H/W padding needs a pre-padded input");
+  }
+  if (d->sh > 2 || d->sw > 2 || d->sh != d->sw) return fail("unsupported spatial stride");
+  if (d->KH > 3 || d->KW > 3 || d->KT > 3) return fail("kernel extent > 3");
+  if (d->up_time == 2 && (d->Cout % 2)) return fail("odd Cout with up_time");
+  return true;
+}
+
+int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
+  const char* why = nullptr;
+  if (!conv_tc_eligible(d, &why)) {
+    set_error("cvvae_conv3d_tc: not eligible: %s", why);
+    return CVVAE_E_UNSUPPORTED;
+  }
+  const cvvae_tensor5& x = d->x;
+  const cvvae_tensor5& y = d->y;
+  ConvTcParams p{};
+  p.B = x.B;
+  p.T_in = x.T;
+  p.Cin = x.C;
+  p.Cout = d->Cout;
+  p.up_time = d->up_time == 2 ? 2 : 1;
+  p.T_out = p.up_time == 2 ? (y.T + 1) / 2 : y.T;
+  p.H_out = y.H;
+  p.W_out = y.W;
+  p.KT = d->KT; p.KH = d->KH; p.KW = d->KW;
+  p.st = d->st; p.sh = d->sh; p.sw = d->sw;
+  p.off_t = d->off_t; p.off_h = d->off_h; p.off_w = d->off_w;
+  p.pad_t = d->pad_t;
+  p.flags = d->flags;
+  p.alpha = d->alpha;
+  p.bias = d->bias;
+  p.residual = d->residual;
+  p.y = y.ptr;
+  p.ys_b = y.s_b; p.ys_t = y.s_t; p.ys_h = y.s_h; p.ys_w = y.s_w; p.ys_c = y.s_c;
+  p.yC = y.C; p.yT = y.T;
+  CVVAE_CHECK_ARG(y.B == x.B, "conv: batch mismatch");
+  CVVAE_CHECK_ARG(y.C == (p.up_time == 2 ? d->Cout / 2 : d->Cout), "conv: y.C %d inconsistent with Cout %d / up_time %d",
+                  y.C, d->Cout, p.up_time);
+  p.vec_ok = (y.s_c == 1) && (y.s_w % 8 == 0) && (y.s_h % 8 == 0) && (y.s_t % 8 == 0) && (y.s_b % 8 == 0) &&
+             (reinterpret_cast<uintptr_t>(y.ptr) % 16 == 0) &&
+             (!d->residual || reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) &&
+             ((p.up_time == 2 ? d->Cout / 2 : d->Cout) % 8 == 0);
+
+  if (d->flags & CVVAE_CONV_OUT_F32) {
+    CVVAE_CHECK_ARG(!d->residual && p.up_time == 1, "conv: fp32 output excludes residual / up_time");
+    p.vec_ok = (y.s_c == 1) && (y.s_w % 4 == 0) && (y.s_h % 4 == 0) && (y.s_t % 4 == 0) && (y.s_b % 4 == 0) &&
+               (reinterpret_cast<uintptr_t>(y.ptr) % 16 == 0);
+  }
+
+  // ---- tiling
+  int N_cta;
+  if (p.Cout >= 256) N_cta = 256;
+  else if (p.Cout > 64) N_cta = 128;
+  else if (p.Cout > 32) N_cta = 64;
+  else if (p.Cout > 16) N_cta = 32;
+  else N_cta = 16;
+  p.N_cta = N_cta;
+  p.n_tiles_n = (p.Cout + N_cta - 1) / N_cta;
+  p.NACC = (512 / N_cta) < 4 ? (512 / N_cta) : 4;
+  p.flat = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1) ? 1 : 0;
+  p.cblocks = (p.Cin + 63) / 64;
+  if (p.flat) {
+    p.TW = 128; p.ROWS = 1; p.TH = 1;
+    p.KHs = 1; p.n_hgroups = 1; p.slab_rows = p.NACC;
+    p.tiles_w = (p.W_out + p.NACC * 128 - 1) / (p.NACC * 128);
+    p.tiles_h = 1;
+  } else {
+    p.KHs = (d->sh == 1) ? d->KH : 1;
+    p.n_hgroups = d->KH / p.KHs;
+    long long best_cost = -1;
+    int best_tw = 16;
+    for (int tw = 8; tw <= 128; tw *= 2) {
+      const int rows = 128 / tw;
+      const int th = rows * p.NACC;
+      if (tw * d->sw > 256 || (th + p.KHs - 1) * d->sh > 256) continue;
+      const long long tiles_w = (p.W_out + tw - 1) / tw;
+      const long long subtiles_h = (p.H_out + rows - 1) / rows;
+      const long long tiles_h = (p.H_out + th - 1) / th;
+      // MMA work ~ sub-tiles; slab traffic ~ (th + halo) rows per tile
+      const long long cost = tiles_w * subtiles_h * 128 * 16 + tiles_w * tiles_h * (th + p.KHs - 1) * tw * 3;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_tw = tw;
+      }
+    }
+    p.TW = best_tw;
+    p.ROWS = 128 / p.TW;
+    p.TH = p.ROWS * p.NACC;
+    p.slab_rows = p.TH + p.KHs - 1;
+    p.tiles_w = (p.W_out + p.TW - 1) / p.TW;
+    p.tiles_h = (p.H_out + p.TH - 1) / p.TH;
+  }
+  p.slab_bytes = p.flat ? static_cast<uint32_t>(p.NACC) * 16384u : static_cast<uint32_t>(p.slab_rows * p.TW) * 128u;
+  p.b_bytes = static_cast<uint32_t>(N_cta) * 128u;
+  p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128, N_cta);
+
+  // ---- shared memory budget: 227 KB - alignment slack - barriers
+  const size_t budget = 232448 - 1024 - 512;
+  int NB = 4;
+  while (NB > 2 && static_cast<size_t>(NB) * p.b_bytes + 2ull * p.slab_bytes > budget) --NB;
+  size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;
+  int NA = static_cast<int>(rest / p.slab_bytes);
+  if (NA > 4) NA = 4;
+  CVVAE_CHECK_ARG(NA >= 2, "conv_tc: slab of %u bytes does not fit the shared-memory budget", p.slab_bytes);
+  // spend what is left on more weight stages
+  while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_bytes <= budget) ++NB;
+  p.NA = NA;
+  p.NB = NB;
+  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 512;
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)x.C, (cuuint64_t)x.W, (cuuint64_t)x.H, (cuuint64_t)x.T, (cuuint64_t)x.B};
+    cuuint64_t strides[4] = {(cuuint64_t)x.s_w * 2, (cuuint64_t)x.s_h * 2, (cuuint64_t)x.s_t * 2, (cuuint64_t)x.s_b * 2};
+    // degenerate dims may carry meaningless strides; TMA wants multiples of 16 and monotone-ish validity
+    for (int i = 0; i < 4; ++i)
+      if (dims[i + 1] == 1 && (strides[i] == 0 || strides[i] % 16)) strides[i] = (cuuint64_t)x.C * 2;
+    cuuint32_t box[5], estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, 1, 1};
+    box[0] = 64;
+    if (p.flat) {
+      box[1] = 128; box[2] = 1;
+    } else {
+      box[1] = (cuuint32_t)(p.TW * d->sw);
+      box[2] = (cuuint32_t)(p.slab_rows * d->sh);
+    }
+    box[3] = 1; box[4] = 1;
+    if (!encode_map(&tmA, x.ptr, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
+  }
+  {
+    const int taps = d->KT * d->KH * d->KW;
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)taps};
+    const cuuint64_t wld = d->w_ld ? (cuuint64_t)d->w_ld : (cuuint64_t)p.Cin;
+    cuuint64_t strides[2] = {wld * 2, wld * p.Cout * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)N_cta, 1}, estr[3] = {1, 1, 1};
+    if (!encode_map(&tmB, d->w, 3, dims, strides, box, estr)) return CVVAE_E_CUDA;
+  }
+
+  const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_h * p.B;
+  CVVAE_CHECK_ARG(grid > 0 && grid < (1ll << 31), "conv_tc: grid size %lld out of range", grid);
+  CVVAE_DISPATCH_DTYPE(d->dtype, {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_set = true;
+    }
+    conv_tc_kernel<DT><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(tmA, tmB, p);
+  });
+  CVVAE_LAUNCH_CHECK();
+  return CVVAE_OK;
+}
+
+}  // namespace cvvae
+
+extern "C" int cvvae_conv3d_tc(const cvvae_conv_desc* d, void* stream) {
+  CVVAE_CHECK_ARG(d && cvvae::tensor_ok(&d->x) && cvvae::tensor_ok(&d->y) && d->w, "cvvae_conv3d_tc: null argument");
+  return cvvae::conv_tc_launch(d, static_cast<cudaStream_t>(stream));
+}

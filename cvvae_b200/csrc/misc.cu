@@ -1,0 +1,182 @@
+// Data-movement kernels either side of the convolutions: nearest x2 upsample, replicate border fill of
+// pre-padded buffers, generic strided copy, and the tile blend of the wrapper.  All HBM-bound,
+// coalesced on the channel axis, 128-bit accesses where the layout allows.
+#include "common.cuh"
+
+namespace cvvae {
+
+struct V5 {
+  void* ptr;
+  int B, T, H, W, C;
+  long long s_b, s_t, s_h, s_w, s_c;
+};
+static V5 mk(const cvvae_tensor5* t) { return V5{t->ptr, t->B, t->T, t->H, t->W, t->C, t->s_b, t->s_t, t->s_h, t->s_w, t->s_c}; }
+
+static bool vec8_ok(const cvvae_tensor5* t) {
+  return t->s_c == 1 && t->C % 8 == 0 && t->s_w % 8 == 0 && t->s_h % 8 == 0 && t->s_t % 8 == 0 && t->s_b % 8 == 0 &&
+         reinterpret_cast<uintptr_t>(t->ptr) % 16 == 0;
+}
+
+// y[b,t,2h+i,2w+j,:] = x[b,t,h,w,:]   (F.interpolate(scale=(1,2,2), mode="nearest"))
+__global__ void __launch_bounds__(256) upsample2x_kernel(const V5 x, const V5 y) {
+  const int vecs = x.C >> 3;
+  const long long n = 1ll * y.B * y.T * y.H * y.W * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vi = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int w = static_cast<int>(r % y.W); r /= y.W;
+    const int h = static_cast<int>(r % y.H); r /= y.H;
+    const int t = static_cast<int>(r % y.T); r /= y.T;
+    const int b = static_cast<int>(r);
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x.ptr) + b * x.s_b + t * x.s_t +
+                                                      (h >> 1) * x.s_h + (w >> 1) * x.s_w) + vi;
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y.ptr) + b * y.s_b + t * y.s_t + h * y.s_h + w * y.s_w) + vi;
+    *dst = __ldg(src);
+  }
+}
+
+// frame of a pre-padded buffer <- nearest interior position
+__global__ void __launch_bounds__(256) replicate_border_kernel(const V5 x) {
+  const int vecs = x.C >> 3;
+  const int per_frame = 2 * x.W + 2 * (x.H - 2);  // border positions of one (b,t) image
+  const long long n = 1ll * x.B * x.T * per_frame * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vi = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int e = static_cast<int>(r % per_frame); r /= per_frame;
+    const int t = static_cast<int>(r % x.T);
+    const int b = static_cast<int>(r / x.T);
+    int h, w;
+    if (e < x.W) { h = 0; w = e; }
+    else if (e < 2 * x.W) { h = x.H - 1; w = e - x.W; }
+    else {
+      const int k = e - 2 * x.W;
+      h = 1 + (k >> 1);
+      w = (k & 1) ? x.W - 1 : 0;
+    }
+    const int hs = min(max(h, 1), x.H - 2), ws = min(max(w, 1), x.W - 2);
+    uint16_t* base = reinterpret_cast<uint16_t*>(x.ptr) + b * x.s_b + t * x.s_t;
+    const uint4 v = *(reinterpret_cast<const uint4*>(base + hs * x.s_h + ws * x.s_w) + vi);
+    *(reinterpret_cast<uint4*>(base + h * x.s_h + w * x.s_w) + vi) = v;
+  }
+}
+
+// element-wise strided copy of 16-bit elements
+__global__ void __launch_bounds__(256) copy5_kernel(const V5 x, const V5 y) {
+  const long long n = 1ll * y.B * y.T * y.H * y.W * y.C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // iterate in the order of the destination's fastest axis to keep stores coalesced
+    long long r = i;
+    int c, w, h, t, b;
+    if (y.s_c == 1) {
+      c = static_cast<int>(r % y.C); r /= y.C;
+      w = static_cast<int>(r % y.W); r /= y.W;
+      h = static_cast<int>(r % y.H); r /= y.H;
+      t = static_cast<int>(r % y.T); r /= y.T;
+      b = static_cast<int>(r);
+    } else {
+      w = static_cast<int>(r % y.W); r /= y.W;
+      h = static_cast<int>(r % y.H); r /= y.H;
+      t = static_cast<int>(r % y.T); r /= y.T;
+      c = static_cast<int>(r % y.C); r /= y.C;
+      b = static_cast<int>(r);
+    }
+    reinterpret_cast<uint16_t*>(y.ptr)[b * y.s_b + t * y.s_t + h * y.s_h + w * y.s_w + c * y.s_c] =
+        reinterpret_cast<const uint16_t*>(x.ptr)[b * x.s_b + t * x.s_t + h * x.s_h + w * x.s_w + c * x.s_c];
+  }
+}
+
+// b[.., i ..] = (1 - i/ov) * a[.., La-ov+i ..] + (i/ov) * b[.., i ..], fp32 math, one rounding
+template <int DT>
+__global__ void __launch_bounds__(256) blend_kernel(const V5 a, const V5 b, int ov, int axis) {
+  using E = Elem<DT>;
+  using T = typename E::T;
+  const int H = axis == 1 ? ov : b.H;
+  const int W = axis == 0 ? ov : b.W;
+  const long long n = 1ll * b.B * b.T * H * W * b.C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    int c, w, h, t, bb;
+    if (b.s_c == 1) {
+      c = static_cast<int>(r % b.C); r /= b.C;
+      w = static_cast<int>(r % W); r /= W;
+      h = static_cast<int>(r % H); r /= H;
+      t = static_cast<int>(r % b.T); r /= b.T;
+      bb = static_cast<int>(r);
+    } else {
+      w = static_cast<int>(r % W); r /= W;
+      h = static_cast<int>(r % H); r /= H;
+      t = static_cast<int>(r % b.T); r /= b.T;
+      c = static_cast<int>(r % b.C); r /= b.C;
+      bb = static_cast<int>(r);
+    }
+    const int k = axis == 0 ? w : h;
+    const float wb = static_cast<float>(k) / static_cast<float>(ov);
+    const int ha = axis == 1 ? a.H - ov + h : h;
+    const int wa = axis == 0 ? a.W - ov + w : w;
+    const float av = E::to_f(reinterpret_cast<const T*>(a.ptr)[bb * a.s_b + t * a.s_t + ha * a.s_h + wa * a.s_w + c * a.s_c]);
+    T* bp = reinterpret_cast<T*>(b.ptr) + bb * b.s_b + t * b.s_t + h * b.s_h + w * b.s_w + c * b.s_c;
+    const float bv = E::to_f(*bp);
+    *bp = E::from_f((1.0f - wb) * av + wb * bv);
+  }
+}
+
+static unsigned grid_for(long long n) {
+  long long blocks = (n + 255) / 256;
+  const long long cap = 16ll * num_sms();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+}  // namespace cvvae
+
+using namespace cvvae;
+
+extern "C" int cvvae_upsample_nearest2x(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream) {
+  (void)dtype;
+  CVVAE_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "cvvae_upsample_nearest2x: null argument");
+  CVVAE_CHECK_ARG(y->B == x->B && y->T == x->T && y->H == 2 * x->H && y->W == 2 * x->W && y->C == x->C,
+                  "cvvae_upsample_nearest2x: shape mismatch");
+  CVVAE_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "cvvae_upsample_nearest2x: needs 16-byte aligned channels-last views");
+  const long long n = 1ll * y->B * y->T * y->H * y->W * (y->C / 8);
+  upsample2x_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(x), mk(y));
+  CVVAE_LAUNCH_CHECK();
+  return CVVAE_OK;
+}
+
+extern "C" int cvvae_replicate_border(const cvvae_tensor5* xpad, int32_t dtype, void* stream) {
+  (void)dtype;
+  CVVAE_CHECK_ARG(tensor_ok(xpad) && xpad->H >= 3 && xpad->W >= 3, "cvvae_replicate_border: bad argument");
+  CVVAE_CHECK_ARG(vec8_ok(xpad), "cvvae_replicate_border: needs a 16-byte aligned channels-last view");
+  const long long n = 1ll * xpad->B * xpad->T * (2 * xpad->W + 2 * (xpad->H - 2)) * (xpad->C / 8);
+  replicate_border_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(xpad));
+  CVVAE_LAUNCH_CHECK();
+  return CVVAE_OK;
+}
+
+extern "C" int cvvae_copy5(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream) {
+  (void)dtype;
+  CVVAE_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "cvvae_copy5: null argument");
+  CVVAE_CHECK_ARG(y->B == x->B && y->T == x->T && y->H == x->H && y->W == x->W && y->C == x->C, "cvvae_copy5: shape mismatch");
+  const long long n = 1ll * y->B * y->T * y->H * y->W * y->C;
+  copy5_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(x), mk(y));
+  CVVAE_LAUNCH_CHECK();
+  return CVVAE_OK;
+}
+
+extern "C" int cvvae_blend(const cvvae_tensor5* a, const cvvae_tensor5* b, int32_t overlap, int32_t axis, int32_t dtype,
+                           void* stream) {
+  CVVAE_CHECK_ARG(tensor_ok(a) && tensor_ok(b) && overlap > 0 && (axis == 0 || axis == 1), "cvvae_blend: bad argument");
+  CVVAE_CHECK_ARG(a->B == b->B && a->T == b->T && a->C == b->C, "cvvae_blend: shape mismatch");
+  if (axis == 0) CVVAE_CHECK_ARG(a->H == b->H && a->W >= overlap && b->W >= overlap, "cvvae_blend: width overlap %d does not fit", overlap);
+  if (axis == 1) CVVAE_CHECK_ARG(a->W == b->W && a->H >= overlap && b->H >= overlap, "cvvae_blend: height overlap %d does not fit", overlap);
+  const long long n = 1ll * b->B * b->T * (axis == 1 ? overlap : b->H) * (axis == 0 ? overlap : b->W) * b->C;
+  CVVAE_DISPATCH_DTYPE(dtype, { blend_kernel<DT><<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(a), mk(b), overlap, axis); });
+  CVVAE_LAUNCH_CHECK();
+  return CVVAE_OK;
+}

@@ -1,0 +1,343 @@
+"""Encoder / Decoder graphs of CV-VAE executed on the hand-written sm_100a kernels.
+
+This is the seam the reference crosses with ``self.encoder(tile)`` / ``self.decoder(tile)``
+(models/modeling_vae.py:162,249).  The graphs follow
+
+  sd21:  models/vae_models.py       Encoder.forward :790-823,   Decoder.forward :960-1002
+  sd3 :  models/vae_models3d_sd3.py Encoder3D.forward :162-208, Decoder3D.forward :323-388
+         with the blocks of models/vae_blocks3d_sd3.py
+
+but nothing of their execution model survives: activations live channels-last ([B,T,H,W,C], 16-bit) from
+the first convolution to the last, every padding is folded into convolution coordinates (TMA
+out-of-bounds fill, time clamp, or - for the sd3 replicate mode - a 1-position frame kept around the
+producer's output), GroupNorm+SiLU is one fused pass, the residual add, the 1x1 shortcut result and
+the temporal interleave of the up-sampler are folded into convolution epilogues, and the caller's
+NCDHW tensors are read / written in place through strided views (no layout copies).
+
+All arithmetic goes through an ``ops`` backend (``cvvae_b200.ops.CudaOps`` in production).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from ._lib import PAD_REPLICATE, PAD_ZERO
+
+
+@dataclass
+class NetConfig:
+    variant: str = "sd21"            # "sd21" | "sd3"
+    in_channels: int = 3
+    out_ch: int = 3
+    z_channels: int = 4
+    widths: Tuple[int, ...] = (128, 256, 512, 512)
+    num_res_blocks: int = 2
+    groups: int = 32
+    double_z: bool = True
+    causal_encoder: bool = True
+    causal_decoder: bool = False
+    half_3d: bool = True
+    encoder_attn_type: str = "vanilla-xformers"
+    decoder_attn_type: str = "spatial-temporal-xformer"
+    mid_block_add_attention: bool = True
+
+    @property
+    def eps(self) -> float:
+        return 1e-5 if self.variant == "sd21" else 1e-6
+
+    @property
+    def moments_channels(self) -> int:
+        return 2 * self.z_channels if self.double_z else self.z_channels
+
+
+class Act:
+    """An activation: logical [B,T,H,W,C] tensor, plus (sd3) the framed buffer it is the interior of."""
+    __slots__ = ("t", "pad")
+
+    def __init__(self, t: torch.Tensor, pad: Optional[torch.Tensor] = None):
+        self.t = t
+        self.pad = pad
+
+
+def prepack_params(state_dict: Dict[str, torch.Tensor], ops, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
+    """Weights -> [taps, Cout, Cin] in the compute dtype; biases and norm parameters -> fp32."""
+    packed = {}
+    for k, v in state_dict.items():
+        if k.endswith(".weight") and v.dim() >= 2:
+            packed[k] = ops.pack_weight(v.detach().to(dtype))
+        else:
+            packed[k] = v.detach().to(torch.float32).contiguous()
+    return packed
+
+
+def _out_len(n: int, k: int, s: int, lo: int, hi: int) -> int:
+    return (n + lo + hi - k) // s + 1
+
+
+class Engine:
+    def __init__(self, cfg: NetConfig, params: Dict[str, torch.Tensor], ops, dtype: torch.dtype):
+        self.cfg = cfg
+        self.p = params
+        self.ops = ops
+        self.dtype = dtype
+        self.sd3 = cfg.variant == "sd3"
+        self.hw_mode = PAD_REPLICATE if self.sd3 else PAD_ZERO
+
+    # ------------------------------------------------------------------ primitives
+    def _tc_ok(self, x: torch.Tensor) -> bool:
+        return x.stride(4) == 1 and x.shape[4] % 8 == 0 and all(s % 8 == 0 for s in x.stride()[:4])
+
+    def _framed(self, a: Act) -> Act:
+        """Give `a` a replicate frame (copy into a framed buffer unless it already lives in one)."""
+        if a.pad is not None:
+            return a
+        B, T, H, W, Cc = a.t.shape
+        pad, inner = self.ops.empty_padded(B, T, H, W, Cc, a.t.dtype, a.t.device)
+        self.ops.copy(a.t, inner)
+        self.ops.replicate_border(pad)
+        return Act(inner, pad)
+
+    def conv(self, a: Act, name: str, *, kernel, stride=(1, 1, 1), pads, pad_t, pad_hw, up_time=1,
+             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> Act:
+        """Convolution with the reference's padding expressed as ((t_lo,t_hi),(h_lo,h_hi),(w_lo,w_hi))."""
+        x = a.t
+        w = self.p[name + ".weight"]
+        b = self.p.get(name + ".bias")
+        B, T, H, W, _ = x.shape
+        (tl, th), (hl, hh), (wl, wh) = pads
+        kt, kh, kw = kernel
+        Co = w.shape[1]
+        To = _out_len(T, kt, stride[0], tl, th)
+        Ho = _out_len(H, kh, stride[1], hl, hh)
+        Wo = _out_len(W, kw, stride[2], wl, wh)
+        if up_time == 2:
+            yshape = (B, 2 * To - 1, Ho, Wo, Co // 2)
+        else:
+            yshape = (B, To, Ho, Wo, Co)
+        if out is None:
+            out = self.ops.empty(yshape, x.dtype, x.device)
+        else:
+            assert tuple(out.shape) == yshape, (tuple(out.shape), yshape)
+        off = (-tl, -hl, -wl)
+        needs_hw_pad = (kh > 1 or kw > 1) and (hl or hh or wl or wh)
+        if pad_hw == PAD_REPLICATE and needs_hw_pad and self._tc_ok(x):
+            a = self._framed(a)
+            x = a.pad
+            off = (-tl, 1 - hl, 1 - wl)
+            pad_hw = PAD_ZERO
+        flat = (kernel == (1, 1, 1) and stride == (1, 1, 1) and x.is_contiguous() and out.is_contiguous()
+                and (residual is None or residual.is_contiguous()) and up_time == 1)
+        if flat:
+            P = B * T * H * W
+            xf = x.view(1, 1, 1, P, x.shape[4])
+            of = out.view(1, 1, 1, P, Co)
+            rf = residual.view(1, 1, 1, P, Co) if residual is not None else None
+            self.ops.conv(xf, w, b, kernel=kernel, residual=rf, out=of)
+        else:
+            self.ops.conv(x, w, b, kernel=kernel, stride=stride, offset=off, pad_t=pad_t, pad_hw=pad_hw,
+                          up_time=up_time, residual=residual, out=out)
+        return Act(out)
+
+    def conv3(self, a: Act, name: str, causal: bool, **kw) -> Act:
+        """3x3x3, stride 1, 'same': CausalConv3d / nn.Conv3d(padding=1) / Conv3d(replicate)."""
+        if self.sd3:
+            tp, pad_t = ((2, 0) if causal else (1, 1)), PAD_REPLICATE
+        else:
+            tp, pad_t = ((2, 0), PAD_REPLICATE) if causal else ((1, 1), PAD_ZERO)
+        return self.conv(a, name, kernel=(3, 3, 3), pads=(tp, (1, 1), (1, 1)), pad_t=pad_t, pad_hw=self.hw_mode, **kw)
+
+    def conv2(self, a: Act, name: str, **kw) -> Act:
+        """Conv2dWithExtraDim 3x3 pad 1 (zeros in both families), per frame."""
+        return self.conv(a, name, kernel=(1, 3, 3), pads=((0, 0), (1, 1), (1, 1)), pad_t=PAD_ZERO, pad_hw=PAD_ZERO, **kw)
+
+    def conv1(self, a: Act, name: str, **kw) -> Act:
+        """1x1(x1) convolution / Linear over channels."""
+        return self.conv(a, name, kernel=(1, 1, 1), pads=((0, 0), (0, 0), (0, 0)), pad_t=PAD_ZERO, pad_hw=PAD_ZERO, **kw)
+
+    def gn(self, a: Act, name: str, *, silu=True, per_frame=False, framed=False) -> Act:
+        x = a.t
+        g, b = self.p[name + ".weight"], self.p[name + ".bias"]
+        if framed:
+            B, T, H, W, Cc = x.shape
+            pad, inner = self.ops.empty_padded(B, T, H, W, Cc, x.dtype, x.device)
+            self.ops.groupnorm(x, g, b, self.cfg.groups, self.cfg.eps, per_frame=per_frame, silu=silu, out=inner)
+            self.ops.replicate_border(pad)
+            return Act(inner, pad)
+        return Act(self.ops.groupnorm(x, g, b, self.cfg.groups, self.cfg.eps, per_frame=per_frame, silu=silu))
+
+    # ------------------------------------------------------------------ blocks
+    def resblock(self, a: Act, p: str, causal: bool) -> Act:
+        """ResnetBlock3D.forward: vae_models.py:390-410 / vae_blocks3d_sd3.py:518-569."""
+        cfg = self.cfg
+        h = self.gn(a, p + ".norm1", framed=self.sd3)
+        h = self.conv3(h, p + ".conv1", causal)
+        # conv2 is a zero-padded per-frame 3x3 when half_3d, else another conv_cls 3x3x3
+        h = self.gn(h, p + ".norm2", framed=(self.sd3 and not cfg.half_3d))
+        sc_name = p + (".conv_shortcut" if self.sd3 else ".nin_shortcut")
+        if (sc_name + ".weight") in self.p:
+            shortcut = self.conv1(Act(a.t), sc_name).t
+        else:
+            shortcut = a.t
+            if not shortcut.is_contiguous():
+                # residual operands share the (dense) output geometry
+                shortcut = self.ops.copy(shortcut, self.ops.empty(shortcut.shape, shortcut.dtype, shortcut.device))
+        if cfg.half_3d:
+            return self.conv2(h, p + ".conv2", residual=shortcut)
+        return self.conv3(h, p + ".conv2", causal, residual=shortcut)
+
+    def spatial_attention(self, hn: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v_name: str) -> torch.Tensor:
+        """softmax(q k^T / sqrt(C)) v per frame, one head (vae_models.py:446-461,500-528; diffusers Attention).
+
+        Three tensor-core GEMMs per frame on the convolution kernel (1x1x1 'flat' problems):
+          v^T = W_v hn^T + b_v   (bias along rows; gives the K-major B operand of the last GEMM directly)
+          S   = q k^T * C^-0.5   (fp32 logits) ; P = softmax(S) (16 bit)
+          O   = P v
+        """
+        ops = self.ops
+        B, T, H, W, Cc = hn.shape
+        N = H * W
+        ld = (N + 7) // 8 * 8
+        wv, bv = self.p[v_name + ".weight"], self.p[v_name + ".bias"]
+        out = ops.empty((B, T, H, W, Cc), hn.dtype, hn.device)
+        wv_act = wv.view(1, 1, 1, Cc, Cc)
+        vT = ops.empty((Cc, ld), hn.dtype, hn.device)
+        S = torch.empty((N, ld), dtype=torch.float32, device=hn.device)
+        P = ops.empty((N, ld), hn.dtype, hn.device)
+        scale = float(Cc) ** -0.5
+        for b in range(B):
+            for t in range(T):
+                hf = hn[b, t].reshape(N, Cc)
+                qf = q[b, t].reshape(1, 1, 1, N, Cc)
+                kf = k[b, t].reshape(1, N, Cc)
+                ops.conv(wv_act, hf.view(1, N, Cc), bv, bias_along_m=True, out=vT[:, :N].unsqueeze(0).unsqueeze(0).unsqueeze(0))
+                ops.conv(qf, kf, None, alpha=scale, out_f32=True, out=S[:, :N].unsqueeze(0).unsqueeze(0).unsqueeze(0))
+                ops.softmax_rows(S, N, P)
+                ops.conv(P[:, :N].unsqueeze(0).unsqueeze(0).unsqueeze(0), vT[:, :N].unsqueeze(0), None, w_ld=ld, cout=Cc,
+                         out=out[b, t].reshape(1, 1, 1, N, Cc))
+        return out
+
+    def attn_sd21(self, a: Act, p: str, attn_type: str) -> Act:
+        """AttnBlock / MemoryEfficientAttnBlock / MemoryEfficientAttnVideoBlock (vae_models.py:427-629)."""
+        if attn_type == "none":
+            return a
+        if attn_type not in ("vanilla", "vanilla-xformers", "spatial-temporal-xformer"):
+            raise NotImplementedError(f"attn_type {attn_type!r} is outside the CV-VAE hot path")
+        x = a.t
+        hn = self.gn(a, p + ".norm", silu=False, per_frame=True)
+        q = self.conv1(hn, p + ".q").t
+        k = self.conv1(hn, p + ".k").t
+        o = Act(self.spatial_attention(hn.t, q, k, p + ".v"))
+        if attn_type != "spatial-temporal-xformer":
+            return self.conv1(o, p + ".proj_out", residual=x)
+        h1 = self.conv1(o, p + ".proj_out")
+        hn2 = Act(self.ops.layernorm(h1.t, self.p[p + ".norm_t.weight"], self.p[p + ".norm_t.bias"], 1e-5))
+        qt = self.conv1(hn2, p + ".q_t").t
+        kt = self.conv1(hn2, p + ".k_t").t
+        vt = self.conv1(hn2, p + ".v_t").t
+        ot = Act(self.ops.attn_temporal(qt, kt, vt))
+        return self.conv1(ot, p + ".proj_out_t", residual=x)
+
+    def attn_sd3(self, a: Act, p: str) -> Act:
+        """AttentionWithExtraDim over diffusers Attention (vae_blocks3d_sd3.py:119-147,805-823)."""
+        x = a.t
+        if not x.is_contiguous():
+            x = self.ops.copy(x, self.ops.empty(x.shape, x.dtype, x.device))
+        hn = self.gn(Act(x), p + ".group_norm", silu=False, per_frame=True)
+        q = self.conv1(hn, p + ".to_q").t
+        k = self.conv1(hn, p + ".to_k").t
+        o = Act(self.spatial_attention(hn.t, q, k, p + ".to_v"))
+        return self.conv1(o, p + ".to_out.0", residual=x)
+
+    # ------------------------------------------------------------------ networks
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """x: [B, C, T, H, W] (any strides) -> moments [B, 2z, T', H/8, W/8] (contiguous NCDHW)."""
+        cfg = self.cfg
+        causal = cfg.causal_encoder
+        L = len(cfg.widths)
+        a = Act(x.permute(0, 2, 3, 4, 1))
+        E = "encoder."
+        h = self.conv3(a, E + "conv_in", causal)
+        for lvl in range(L):
+            for b in range(cfg.num_res_blocks):
+                name = f"{E}down_blocks.{lvl}.resnets.{b}" if self.sd3 else f"{E}down.{lvl}.block.{b}"
+                h = self.resblock(h, name, causal)
+            if lvl != L - 1:
+                st = 2 if lvl % 2 == 0 else 1
+                if self.sd3:
+                    # Downsample3D -> conv_cls(k3, stride, padding=1): vae_blocks3d_sd3.py:200-210
+                    tp = (2, 0) if causal else (1, 1)
+                    h = self.conv(h, f"{E}down_blocks.{lvl}.downsamplers.0.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
+                                  pads=(tp, (1, 1), (1, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_REPLICATE)
+                else:
+                    # Downsample3D.forward vae_models.py:251-263: zero pad right/bottom, replicate 2 frames in front
+                    h = self.conv(h, f"{E}down.{lvl}.downsample.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
+                                  pads=((2, 0), (0, 1), (0, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_ZERO)
+        if self.sd3:
+            h = self.resblock(h, E + "mid_block.resnets.0", causal)
+            if cfg.mid_block_add_attention:
+                h = self.attn_sd3(h, E + "mid_block.attentions.0")
+            h = self.resblock(h, E + "mid_block.resnets.1", causal)
+            h = self.gn(h, E + "conv_norm_out", framed=True)
+        else:
+            h = self.resblock(h, E + "mid.block_1", causal)
+            h = self.attn_sd21(h, E + "mid.attn_1", cfg.encoder_attn_type)
+            h = self.resblock(h, E + "mid.block_2", causal)
+            h = self.gn(h, E + "norm_out")
+        B, T, H, W, _ = h.t.shape
+        out = torch.empty((B, cfg.moments_channels, T, H, W), dtype=x.dtype, device=x.device)
+        self.conv3(h, E + "conv_out", causal, out=out.permute(0, 2, 3, 4, 1))
+        return out
+
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        """z: [B, zc, T', h, w] -> x [B, 3, 4(T'-1)+1, 8h, 8w] (contiguous NCDHW)."""
+        cfg = self.cfg
+        causal = cfg.causal_decoder
+        L = len(cfg.widths)
+        D = "decoder."
+        a = Act(z.permute(0, 2, 3, 4, 1))
+        h = self.conv3(a, D + "conv_in", causal)
+        if self.sd3:
+            h = self.resblock(h, D + "mid_block.resnets.0", causal)
+            if cfg.mid_block_add_attention:
+                h = self.attn_sd3(h, D + "mid_block.attentions.0")
+            h = self.resblock(h, D + "mid_block.resnets.1", causal)
+        else:
+            h = self.resblock(h, D + "mid.block_1", causal)
+            h = self.attn_sd21(h, D + "mid.attn_1", cfg.decoder_attn_type)
+            h = self.resblock(h, D + "mid.block_2", causal)
+        for i in range(L):
+            lvl = L - 1 - i  # sd21 names levels bottom-up, sd3 names blocks in execution order
+            for b in range(cfg.num_res_blocks + 1):
+                name = f"{D}up_blocks.{i}.resnets.{b}" if self.sd3 else f"{D}up.{lvl}.block.{b}"
+                h = self.resblock(h, name, causal)
+            if i != L - 1:
+                up_time = 2 if (lvl % 2 == 1) else 1  # == (i % 2 == 0) for L = 4
+                if self.sd3:
+                    up_time = 2 if (i % 2 == 0) else 1
+                h = self.upsample(h, f"{D}up_blocks.{i}.upsamplers.0.conv" if self.sd3 else f"{D}up.{lvl}.upsample.conv",
+                                  up_time, causal)
+        h = self.gn(h, D + ("conv_norm_out" if self.sd3 else "norm_out"), framed=self.sd3)
+        B, T, H, W, _ = h.t.shape
+        out = torch.empty((B, cfg.out_ch, T, H, W), dtype=z.dtype, device=z.device)
+        self.conv3(h, D + "conv_out", causal, out=out.permute(0, 2, 3, 4, 1))
+        return out
+
+    def upsample(self, a: Act, name: str, up_time: int, causal: bool) -> Act:
+        """Upsample3D.forward (vae_models.py:214-235, vae_blocks3d_sd3.py:314-364): nearest x(1,2,2), 3x3x3 conv
+        to C*up_time channels, channel->time interleave and drop of frame 0 (both in the conv epilogue)."""
+        x = a.t
+        B, T, H, W, Cc = x.shape
+        if self.sd3:
+            pad, inner = self.ops.empty_padded(B, T, 2 * H, 2 * W, Cc, x.dtype, x.device)
+            self.ops.upsample2x(x, inner)
+            self.ops.replicate_border(pad)
+            u = Act(inner, pad)
+            tp = (2, 0) if causal else (1, 1)
+            return self.conv(u, name, kernel=(3, 3, 3), pads=(tp, (1, 1), (1, 1)), pad_t=PAD_REPLICATE,
+                             pad_hw=PAD_REPLICATE, up_time=up_time)
+        u = Act(self.ops.upsample2x(x))
+        # NB the sd21 Decoder never forwards `causal` to Upsample3D (vae_models.py:936): always replicate (1,1)
+        return self.conv(u, name, kernel=(3, 3, 3), pads=((1, 1), (1, 1), (1, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_ZERO,
+                         up_time=up_time)

@@ -1,0 +1,422 @@
+"""Drop-in ``CVVAEModel`` / ``CVVAESD3Model``: the reference's Python surface over the sm_100a engine.
+
+Mirrors models/modeling_vae.py of the reference - same constructor keyword arguments and defaults
+(:23-51, :347-381), ``config`` attribute/dict access, ``from_pretrained(path, subfolder=, torch_dtype=)``
+reading ``config.json`` + ``diffusion_pytorch_model.safetensors``, ``encode()`` / ``decode()`` /
+``forward()`` signatures and return objects (:114-142, :212-228, :298-319), 4-D input handling, and the
+exact temporal-chunk (:193-210, :279-296) / spatial-tile (:144-191, :230-277) / in-place linear blend
+(:321-341) decomposition, which is part of the function being computed (GroupNorm statistics are per
+chunk x tile).  ``cvvae_inference_video.py`` and the SD pipelines call it unchanged.
+
+The arithmetic runs in hand-written CUDA (cvvae_b200/csrc) through the C ABI; this file holds no
+PyTorch compute beyond slicing / concatenation of tile results and the tiny posterior helpers.
+"""
+from __future__ import annotations
+
+import inspect
+import json
+import math
+import os
+import weakref
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine, NetConfig, prepack_params
+from .params import ParamTree, build_param_tree, param_shapes
+
+
+class FrozenConfig(dict):
+    """``model.config.key`` and ``model.config["key"]`` (diffusers FrozenDict behaviour)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+@dataclass
+class DecoderOutput:
+    sample: torch.Tensor
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+@dataclass
+class AutoencoderKLOutput:
+    latent_dist: "DiagonalGaussianDistribution"
+
+    def __getitem__(self, i):
+        return (self.latent_dist,)[i]
+
+
+class DiagonalGaussianDistribution:
+    """Posterior wrapper (diffusers' class; reference twin lvdm/modules/distributions/distributions.py:24-73)."""
+
+    def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        eps = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
+        return self.mean + self.std * eps
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+def _register_config(init):
+    """Record constructor kwargs (with defaults) like diffusers' @register_to_config."""
+    sig = inspect.signature(init)
+
+    def wrapper(self, *args, **kwargs):
+        bound = sig.bind(self, *args, **kwargs)
+        bound.apply_defaults()
+        cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+        nn.Module.__init__(self)
+        object.__setattr__(self, "_config", FrozenConfig(cfg))
+        init(self, *args, **kwargs)
+
+    wrapper.__signature__ = sig
+    wrapper.__doc__ = init.__doc__
+    return wrapper
+
+
+class _NetHandle(ParamTree):
+    """`model.encoder` / `model.decoder`: parameter owner + callable that runs the CUDA engine."""
+
+    def __init__(self, owner: nn.Module, which: str):
+        super().__init__()
+        object.__setattr__(self, "_owner_ref", weakref.ref(owner))
+        self._which = which
+
+    def forward(self, x: torch.Tensor, **unused) -> torch.Tensor:
+        return self._owner_ref()._run_net(self._which, x)
+
+
+class _CVVAEBase(nn.Module):
+    config_name = "config.json"
+    weights_name = "diffusion_pytorch_model.safetensors"
+    _ops_factory = None  # tests may inject a CPU restatement of the operator set; production leaves None
+
+    # ---- construction helpers -------------------------------------------------
+    def _setup(self, net: NetConfig, en_de_n_frames_a_time, time_n_compress, spatial_n_compress, tile_spatial_size,
+               num_video_frames, tile_overlap_ratio, reshape_z_dim_to_4, reshape_x_dim_to_4):
+        self.net = net
+        # `self.encoder(tile)` / `self.decoder(tile)` stay callable: the operator seam of the reference
+        # (modeling_vae.py:162,249).  The handles own the parameters under the reference's key names.
+        self.add_module("encoder", _NetHandle(self, "encode"))
+        self.add_module("decoder", _NetHandle(self, "decode"))
+        build_param_tree(self, param_shapes(net))
+        # derived attributes: modeling_vae.py:84-112
+        if en_de_n_frames_a_time is not None:
+            assert time_n_compress is not None
+            assert en_de_n_frames_a_time % time_n_compress == 0
+            self.encode_n_frames_a_time = en_de_n_frames_a_time
+            self.decode_n_frames_a_time = en_de_n_frames_a_time // time_n_compress
+        else:
+            self.encode_n_frames_a_time = None
+            self.decode_n_frames_a_time = None
+        if num_video_frames is not None:
+            assert time_n_compress is not None
+            self.num_video_frames = num_video_frames
+            self.num_latent_frames = 1 + (num_video_frames - 1) // time_n_compress
+        else:
+            self.num_video_frames = None
+            self.num_latent_frames = None
+        if tile_spatial_size is not None:
+            assert spatial_n_compress is not None and tile_overlap_ratio is not None
+            self.pixel_tile_size = tile_spatial_size
+            self.latent_tile_size = tile_spatial_size // spatial_n_compress
+            self.tile_overlap_ratio = tile_overlap_ratio
+        else:
+            self.pixel_tile_size = None
+            self.latent_tile_size = None
+            self.tile_overlap_ratio = None
+        self.reshape_z_dim_to_4 = reshape_z_dim_to_4
+        self.reshape_x_dim_to_4 = reshape_x_dim_to_4
+        self._engine_cache = None
+        self.requires_grad_(False)
+        self.eval()
+
+    @property
+    def config(self) -> FrozenConfig:
+        return self._config
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    # ---- checkpoint I/O (diffusers ModelMixin surface used by the reference scripts) ----------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None,
+                        torch_dtype: Optional[torch.dtype] = None, **unused):
+        d = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        with open(os.path.join(d, cls.config_name)) as f:
+            raw = json.load(f)
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        cfg = {k: v for k, v in raw.items() if k in accepted}
+        model = cls(**cfg)
+        st = os.path.join(d, cls.weights_name)
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(d, "diffusion_pytorch_model.bin"), map_location="cpu")
+        model.load_state_dict(sd, strict=True)
+        if torch_dtype is not None:
+            model = model.to(torch_dtype)
+        return model
+
+    def save_pretrained(self, save_directory: str):
+        from safetensors.torch import save_file
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = dict(self.config)
+        cfg["_class_name"] = type(self).__name__
+        with open(os.path.join(save_directory, self.config_name), "w") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.contiguous() for k, v in self.state_dict().items()}, os.path.join(save_directory, self.weights_name))
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self._engine_cache = None
+        # the sd3 reference registers the same down-sampler conv under two names in some diffusers versions;
+        # tolerate the alias when present
+        sd = {k: v for k, v in state_dict.items() if ".Conv2d_0." not in k}
+        return super().load_state_dict(sd, strict=strict, assign=assign)
+
+    def _apply(self, fn, *a, **k):
+        self._engine_cache = None
+        return super()._apply(fn, *a, **k)
+
+    # ---- engine ---------------------------------------------------------------
+    def _engine(self) -> Engine:
+        p0 = next(self.parameters())
+        key = (p0.device, p0.dtype)
+        if self._engine_cache is None or self._engine_cache[0] != key:
+            if self._ops_factory is not None:
+                ops = self._ops_factory()
+            else:
+                if p0.device.type != "cuda":
+                    raise RuntimeError("cvvae_b200 runs on CUDA (sm_100a) only: move the model with .cuda(); "
+                                       "there is no CPU or PyTorch fallback path")
+                if p0.dtype not in (torch.float16, torch.bfloat16):
+                    raise RuntimeError(f"cvvae_b200 computes in float16/bfloat16; model dtype is {p0.dtype} - call .half()")
+                from .ops import CudaOps
+                ops = CudaOps()
+            packed = prepack_params(self.state_dict(), ops, p0.dtype)
+            self._engine_cache = (key, Engine(self.net, packed, ops, p0.dtype))
+        return self._engine_cache[1]
+
+    def _run_net(self, which: str, x: torch.Tensor) -> torch.Tensor:
+        self._check_input(x)
+        eng = self._engine()
+        return eng.encode(x) if which == "encode" else eng.decode(x)
+
+    def _check_input(self, x):
+        if x.dtype != self.dtype:
+            raise RuntimeError(f"Input type ({x.dtype}) and model weight type ({self.dtype}) should be the same")
+        if x.device != self.device:
+            raise RuntimeError(f"Input device ({x.device}) and model device ({self.device}) should be the same")
+
+    # ---- forward: modeling_vae.py:114-142 ---------------------------------------
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, sample_posterior: bool = False, return_dict: bool = True,
+                generator: Optional[torch.Generator] = None, num_frames: int = None):
+        posterior = self.encode(sample).latent_dist
+        z = posterior.sample(generator=generator) if sample_posterior else posterior.mode()
+        dec = self.decode(z, num_frames=num_frames).sample
+        if not return_dict:
+            return (dec,)
+        return DecoderOutput(sample=dec)
+
+    # ---- tiling: modeling_vae.py:144-191, 230-277 -------------------------------
+    def _blend_v(self, a: torch.Tensor, b: torch.Tensor, overlap: int) -> torch.Tensor:
+        self._engine().ops.blend(a.permute(0, 2, 3, 4, 1), b.permute(0, 2, 3, 4, 1), overlap, 1)
+        return b
+
+    def _blend_h(self, a: torch.Tensor, b: torch.Tensor, overlap: int) -> torch.Tensor:
+        self._engine().ops.blend(a.permute(0, 2, 3, 4, 1), b.permute(0, 2, 3, 4, 1), overlap, 0)
+        return b
+
+    # public names of the reference (:321-341)
+    def blend_h(self, a, b, overlap_size):
+        return self._blend_h(a, b, overlap_size)
+
+    def blend_v(self, a, b, overlap_size):
+        return self._blend_v(a, b, overlap_size)
+
+    def _spatial_tiled(self, x: torch.Tensor, fn, in_tile: Optional[int], out_tile: Optional[int]) -> torch.Tensor:
+        if in_tile is None:
+            return fn(x)
+        ratio = self.tile_overlap_ratio
+        in_stride = round(in_tile * (1 - ratio))
+        out_overlap = round(out_tile * ratio)
+        out_stride = out_tile - out_overlap
+        rows = []
+        for i in range(0, x.shape[3], in_stride):
+            cols = []
+            for j in range(0, x.shape[4], in_stride):
+                cols.append(fn(x[:, :, :, i:i + in_tile, j:j + in_tile]))
+                if j + in_tile >= x.shape[4]:
+                    break
+            rows.append(cols)
+            if i + in_tile >= x.shape[3]:
+                break
+        if len(rows) == 1 and len(rows[0]) == 1:
+            return rows[0][0]
+        # blend against the already blended upper / left neighbours, in place (reference order)
+        for i, cols in enumerate(rows):
+            for j, tile in enumerate(cols):
+                if i > 0:
+                    self._blend_v(rows[i - 1][j], tile, out_overlap)
+                if j > 0:
+                    self._blend_h(cols[j - 1], tile, out_overlap)
+        out_rows = []
+        for i, cols in enumerate(rows):
+            cropped = []
+            for j, tile in enumerate(cols):
+                if i < len(rows) - 1:
+                    tile = tile[:, :, :, :out_stride, :]
+                if j < len(cols) - 1:
+                    tile = tile[:, :, :, :, :out_stride]
+                cropped.append(tile)
+            out_rows.append(torch.cat(cropped, dim=4))
+        return torch.cat(out_rows, dim=3)
+
+    def spatial_tiled_encode(self, x):
+        return self._spatial_tiled(x, self.encoder, self.pixel_tile_size, self.latent_tile_size)
+
+    def spatial_tiled_decode(self, z, **kwargs):
+        return self._spatial_tiled(z, self.decoder, self.latent_tile_size, self.pixel_tile_size)
+
+    # ---- chunking: modeling_vae.py:193-210, 279-296 ---------------------------------
+    @staticmethod
+    def _chunks(n_frames: int, stride: int):
+        n_rounds = math.ceil((n_frames - 1) / stride)
+        n_rounds = 1 if n_rounds == 0 else n_rounds
+        return [(n * stride, (n + 1) * stride + 1) for n in range(n_rounds)]
+
+    def tiled_encode(self, x):
+        if self.encode_n_frames_a_time is None:
+            return self.spatial_tiled_encode(x)
+        assert x.dim() == 5
+        zs = []
+        for n, (a, b) in enumerate(self._chunks(x.shape[2], self.encode_n_frames_a_time)):
+            z = self.spatial_tiled_encode(x[:, :, a:b])
+            zs.append(z if n == 0 else z[:, :, 1:])
+        return zs[0] if len(zs) == 1 else torch.cat(zs, dim=2)
+
+    def tiled_decode(self, z, **kwargs):
+        if self.decode_n_frames_a_time is None:
+            return self.spatial_tiled_decode(z, **kwargs)
+        assert z.dim() == 5
+        xs = []
+        for n, (a, b) in enumerate(self._chunks(z.shape[2], self.decode_n_frames_a_time)):
+            x = self.spatial_tiled_decode(z[:, :, a:b], **kwargs)
+            xs.append(x if n == 0 else x[:, :, 1:])
+        return xs[0] if len(xs) == 1 else torch.cat(xs, dim=2)
+
+    # ---- encode / decode: modeling_vae.py:212-228, 298-319 ---------------------------
+    def _maybe_offload_hook(self):
+        hook = getattr(self, "_hf_hook", None)  # accelerate offload hook pass-through (apply_forward_hook)
+        if hook is not None and hasattr(hook, "pre_forward"):
+            hook.pre_forward(self)
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        self._maybe_offload_hook()
+        if x.dim() == 4:
+            if self.num_video_frames is not None:
+                t = self.num_video_frames
+                bt, c, h, w = x.shape
+                x = x.reshape(bt // t, t, c, h, w).permute(0, 2, 1, 3, 4)
+            else:
+                x = x.unsqueeze(2)
+        moments = self.tiled_encode(x)
+        posterior = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior)
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, num_frames: int = None, return_dict: bool = True):
+        self._maybe_offload_hook()
+        if z.dim() == 4:
+            t = num_frames if num_frames is not None else self.num_latent_frames
+            if t is not None:
+                bt, c, h, w = z.shape
+                z = z.reshape(bt // t, t, c, h, w).permute(0, 2, 1, 3, 4)
+            else:
+                z = z.unsqueeze(2)
+        x = self.tiled_decode(z)
+        if self.reshape_x_dim_to_4:
+            b, c, t, h, w = x.shape
+            x = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+        if not return_dict:
+            return (x,)
+        return DecoderOutput(sample=x)
+
+
+class CVVAEModel(_CVVAEBase):
+    """SD2.1-compatible CV-VAE (4-channel latent); reference models/modeling_vae.py:20-341."""
+
+    @_register_config
+    def __init__(self, double_z=True, z_channels=4, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+                 num_res_blocks=2, attn_resolutions=[], dropout=0.0, use_3d_conv=True, half_3d=True,
+                 causal_encoder=True, causal_decoder=False, encoder_attn_type="vanilla-xformers",
+                 decoder_attn_type="spatial-temporal-xformer", scaling_factor: float = 0.18215,
+                 force_upcast: float = True, en_de_n_frames_a_time: Optional[int] = 16,
+                 time_n_compress: Optional[int] = 4, spatial_n_compress: Optional[int] = 8,
+                 tile_spatial_size: Optional[int] = 576, num_video_frames: Optional[int] = None,
+                 tile_overlap_ratio: Optional[float] = 0.2222, reshape_z_dim_to_4: bool = False,
+                 reshape_x_dim_to_4: bool = False):
+        if not use_3d_conv:
+            raise NotImplementedError("use_3d_conv=False is not a CV-VAE configuration (no shipped checkpoint uses it)")
+        if attn_resolutions:
+            raise NotImplementedError("attn_resolutions != [] is not used by any CV-VAE checkpoint")
+        if dropout:
+            raise NotImplementedError("dropout is a training-only setting")
+        net = NetConfig(variant="sd21", in_channels=in_channels, out_ch=out_ch, z_channels=z_channels,
+                        widths=tuple(ch * m for m in ch_mult), num_res_blocks=num_res_blocks, double_z=double_z,
+                        causal_encoder=causal_encoder, causal_decoder=causal_decoder, half_3d=half_3d,
+                        encoder_attn_type=encoder_attn_type, decoder_attn_type=decoder_attn_type)
+        self._setup(net, en_de_n_frames_a_time, time_n_compress, spatial_n_compress, tile_spatial_size,
+                    num_video_frames, tile_overlap_ratio, reshape_z_dim_to_4, reshape_x_dim_to_4)
+
+
+class CVVAESD3Model(_CVVAEBase):
+    """SD3-compatible CV-VAE (16-channel latent); reference models/modeling_vae.py:344-667."""
+
+    @_register_config
+    def __init__(self, in_channels: int = 3, out_channels: int = 16,
+                 down_block_types=["DownEncoderBlock3D"] * 4, up_block_types=["UpDecoderBlock3D"] * 4,
+                 block_out_channels=[128, 256, 512, 512], layers_per_block=2, norm_num_groups=32, act_fn="silu",
+                 double_z=True, mid_block_add_attention=True, causal_encoder=True, causal_decoder=False,
+                 half_3d=True, en_de_n_frames_a_time: Optional[int] = 16, time_n_compress: Optional[int] = 4,
+                 spatial_n_compress: Optional[int] = 8, tile_spatial_size: Optional[int] = 576,
+                 num_video_frames: Optional[int] = None, tile_overlap_ratio: Optional[float] = 0.2222,
+                 reshape_z_dim_to_4: bool = False, reshape_x_dim_to_4: bool = False):
+        if act_fn not in ("silu", "swish"):
+            raise NotImplementedError(f"act_fn {act_fn!r}: CV-VAE uses SiLU")
+        if any(t != "DownEncoderBlock3D" for t in down_block_types) or any(t != "UpDecoderBlock3D" for t in up_block_types):
+            raise ValueError("unknown block type")
+        net = NetConfig(variant="sd3", in_channels=in_channels, out_ch=in_channels, z_channels=out_channels,
+                        widths=tuple(block_out_channels), num_res_blocks=layers_per_block, groups=norm_num_groups,
+                        double_z=double_z, causal_encoder=causal_encoder, causal_decoder=causal_decoder,
+                        half_3d=half_3d, mid_block_add_attention=mid_block_add_attention)
+        self._setup(net, en_de_n_frames_a_time, time_n_compress, spatial_n_compress, tile_spatial_size,
+                    num_video_frames, tile_overlap_ratio, reshape_z_dim_to_4, reshape_x_dim_to_4)

@@ -1,0 +1,178 @@
+"""Torch-tensor facing wrappers of the C ABI (device pointers + the current CUDA stream in, nothing else).
+
+Every activation is a torch tensor viewed as logical ``[B, T, H, W, C]`` with arbitrary strides
+(channels-last buffers are contiguous in that view; a caller's NCDHW tensor is passed as
+``x.permute(0, 2, 3, 4, 1)`` without a copy).  PyTorch is used for memory and streams only.
+
+``CudaOps`` is the one production backend.  The engine takes the backend as an argument so that the
+CPU test-suite can drive the same graph code with a torch restatement of each operator
+(``tests/fake_ops.py``); the product never selects anything but ``CudaOps``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float16: L.F16, torch.bfloat16: L.BF16}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise L.CvvaeError(f"cvvae_b200 computes in float16 or bfloat16 only, got {dt}; call .half() or .bfloat16()")
+
+
+def _t5(t: torch.Tensor) -> L.Tensor5:
+    assert t.dim() == 5, t.shape
+    s = t.stride()
+    return L.Tensor5(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3], t.shape[4], s[0], s[1], s[2], s[3], s[4])
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class CudaOps:
+    """The production operator set: every method is one (or two) hand-written sm_100a kernels."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = L.load()
+
+    # ------------------------------------------------------------------ memory (plumbing)
+    @staticmethod
+    def empty(shape: Sequence[int], dtype, device) -> torch.Tensor:
+        return torch.empty(tuple(shape), dtype=dtype, device=device)
+
+    def empty_padded(self, B, T, H, W, Cc, dtype, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """A buffer with a 1-position frame in H and W; returns (padded, interior view)."""
+        p = torch.empty((B, T, H + 2, W + 2, Cc), dtype=dtype, device=device)
+        return p, p[:, :, 1:-1, 1:-1, :]
+
+    # ------------------------------------------------------------------ convolution / GEMM
+    def pack_weight(self, w: torch.Tensor) -> torch.Tensor:
+        """[Cout, Cin, *k] (PyTorch) -> [taps, Cout, Cin] in the same 16-bit dtype."""
+        w = w.contiguous()
+        co, ci = w.shape[0], w.shape[1]
+        taps = 1
+        for k in w.shape[2:]:
+            taps *= k
+        out = torch.empty((taps, co, ci), dtype=w.dtype, device=w.device)
+        L.check(self.lib.cvvae_pack_conv_weight(w.data_ptr(), out.data_ptr(), co, ci, taps, dtype_code(w.dtype), _stream(w)),
+                "cvvae_pack_conv_weight")
+        return out
+
+    def conv(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, kernel=(1, 1, 1),
+             stride=(1, 1, 1), offset=(0, 0, 0), pad_t=L.PAD_ZERO, pad_hw=L.PAD_ZERO, up_time=1,
+             residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
+             out_f32: bool = False, bias_along_m: bool = False, w_ld: int = 0, cout: Optional[int] = None,
+             force: Optional[str] = None) -> torch.Tensor:
+        """y = alpha * conv(x, w) + bias + residual.  ``w`` is packed [taps, Cout, Cin(ld)]."""
+        B, T, H, W, Ci = x.shape
+        kt, kh, kw = kernel
+        st, sh, sw = stride
+        ot, oh, ow = offset
+        Co = cout if cout is not None else w.shape[1]
+        assert w.shape[0] == kt * kh * kw, (w.shape, kernel)
+        if out is None:
+            # PyTorch conv arithmetic with the padding implied by the offsets: out = floor((in + pad - k)/s) + 1,
+            # where the engine always passes offsets so that the reference's output extents result.
+            raise ValueError("conv(): the caller provides `out` (the engine knows the reference's output extents)")
+        d = L.ConvDesc()
+        d.x = _t5(x)
+        d.y = _t5(out)
+        d.w = w.data_ptr()
+        d.w_ld = w_ld
+        d.bias = _ptr(bias)
+        d.residual = _ptr(residual)
+        d.Cout = Co
+        d.KT, d.KH, d.KW = kt, kh, kw
+        d.st, d.sh, d.sw = st, sh, sw
+        d.off_t, d.off_h, d.off_w = ot, oh, ow
+        d.pad_t, d.pad_hw = pad_t, pad_hw
+        d.up_time = up_time
+        d.dtype = dtype_code(x.dtype)
+        d.flags = (L.CONV_BIAS_ALONG_M if bias_along_m else 0) | (L.CONV_OUT_F32 if out_f32 else 0)
+        d.alpha = alpha
+        if residual is not None:
+            assert residual.shape == out.shape and residual.stride() == out.stride(), "residual must share y's geometry"
+        fn = {None: self.lib.cvvae_conv3d, "tc": self.lib.cvvae_conv3d_tc, "direct": self.lib.cvvae_conv3d_direct}[force]
+        L.check(fn(C.byref(d), _stream(x)), "cvvae_conv3d")
+        return out
+
+    # ------------------------------------------------------------------ normalisation
+    def groupnorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *,
+                  per_frame: bool = False, silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, T = x.shape[0], x.shape[1]
+        units = B * T if per_frame else B
+        stats = torch.empty((units, groups, 2), dtype=torch.float64, device=x.device)
+        if out is None:
+            out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        dt = dtype_code(x.dtype)
+        xs, ys = _t5(x), _t5(out)
+        L.check(self.lib.cvvae_groupnorm_stats(C.byref(xs), groups, int(per_frame), stats.data_ptr(), dt, _stream(x)),
+                "cvvae_groupnorm_stats")
+        L.check(self.lib.cvvae_groupnorm_apply(C.byref(xs), C.byref(ys), groups, int(per_frame), stats.data_ptr(),
+                                               gamma.data_ptr(), beta.data_ptr(), eps, int(silu), dt, _stream(x)),
+                "cvvae_groupnorm_apply")
+        return out
+
+    def layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        xs, ys = _t5(x), _t5(out)
+        L.check(self.lib.cvvae_layernorm(C.byref(xs), C.byref(ys), gamma.data_ptr(), beta.data_ptr(), eps,
+                                         dtype_code(x.dtype), _stream(x)), "cvvae_layernorm")
+        return out
+
+    # ------------------------------------------------------------------ attention helpers
+    def softmax_rows(self, s: torch.Tensor, cols: int, out: torch.Tensor) -> torch.Tensor:
+        """s: fp32 [rows, ld_s]; out: 16-bit [rows, ld_p]; softmax over the first `cols` of each row."""
+        assert s.dtype == torch.float32 and s.dim() == 2 and out.dim() == 2 and s.stride(1) == 1 and out.stride(1) == 1
+        L.check(self.lib.cvvae_softmax_rows(s.data_ptr(), s.stride(0), out.data_ptr(), out.stride(0), s.shape[0], cols,
+                                            dtype_code(out.dtype), _stream(s)), "cvvae_softmax_rows")
+        return out
+
+    def attn_temporal(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+        a, b, c, o = _t5(q), _t5(k), _t5(v), _t5(out)
+        L.check(self.lib.cvvae_attn_temporal(C.byref(a), C.byref(b), C.byref(c), C.byref(o), dtype_code(q.dtype), _stream(q)),
+                "cvvae_attn_temporal")
+        return out
+
+    # ------------------------------------------------------------------ data movement
+    def upsample2x(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, T, H, W, Cc = x.shape
+        if out is None:
+            out = torch.empty((B, T, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
+        xs, ys = _t5(x), _t5(out)
+        L.check(self.lib.cvvae_upsample_nearest2x(C.byref(xs), C.byref(ys), dtype_code(x.dtype), _stream(x)),
+                "cvvae_upsample_nearest2x")
+        return out
+
+    def replicate_border(self, xpad: torch.Tensor) -> None:
+        xs = _t5(xpad)
+        L.check(self.lib.cvvae_replicate_border(C.byref(xs), dtype_code(xpad.dtype), _stream(xpad)), "cvvae_replicate_border")
+
+    def copy(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        xs, ys = _t5(x), _t5(out)
+        L.check(self.lib.cvvae_copy5(C.byref(xs), C.byref(ys), dtype_code(x.dtype), _stream(x)), "cvvae_copy5")
+        return out
+
+    def blend(self, a: torch.Tensor, b: torch.Tensor, overlap: int, axis: int) -> torch.Tensor:
+        """In place on b (logical [B,T,H,W,C] views): axis 0 = width (blend_h), 1 = height (blend_v)."""
+        xs, ys = _t5(a), _t5(b)
+        L.check(self.lib.cvvae_blend(C.byref(xs), C.byref(ys), overlap, axis, dtype_code(b.dtype), _stream(b)), "cvvae_blend")
+        return b
+
+    def launch_count(self) -> int:
+        return int(self.lib.cvvae_launch_count())

@@ -1,0 +1,159 @@
+/*
+ * cvvae_b200 - C ABI of the B200-native CV-VAE encode()/decode() hot path.
+ *
+ * The reference (AILab-CVC/CV-VAE) is pure Python on PyTorch and has no FFI of its own; the seam this
+ * library replaces is the `nn.Module.__call__` operator boundary inside `self.encoder(x)` /
+ * `self.decoder(z)` (models/modeling_vae.py:162,249), i.e. the PyTorch library ops listed below.  A
+ * reference-side binding is a ctypes stub that passes `tensor.data_ptr()` and the current CUDA stream
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative CVVAE_E_* code otherwise; the message of the
+ *     last failure on the calling thread is available from cvvae_last_error().  Nothing aborts or throws.
+ *   - no allocation inside: the caller owns inputs, outputs and workspaces (device pointers).
+ *   - every call is asynchronous on the `stream` it is given (a cudaStream_t passed as void*).
+ *   - activations are channels-last: element (b,t,h,w,c) lives at b*s_b + t*s_t + h*s_h + w*s_w + c*s_c
+ *     (strides in ELEMENTS).  The tensor-core path needs s_c == 1 on its input.
+ *   - dtype: CVVAE_F16 or CVVAE_BF16 for activations and packed weights; bias / norm parameters /
+ *     statistics are fp32 (statistics accumulators fp64).
+ */
+#ifndef CVVAE_B200_H_
+#define CVVAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVVAE_ABI_VERSION 1
+
+enum { CVVAE_F16 = 0, CVVAE_BF16 = 1 };
+enum { CVVAE_PAD_ZERO = 0, CVVAE_PAD_REPLICATE = 1 };
+enum {
+  CVVAE_OK = 0,
+  CVVAE_E_ARG = -1,      /* invalid / unsupported argument combination */
+  CVVAE_E_CUDA = -2,     /* CUDA runtime / driver error                */
+  CVVAE_E_UNSUPPORTED = -3
+};
+enum {
+  CVVAE_CONV_BIAS_ALONG_M = 1, /* bias indexed by flattened output position instead of channel */
+  CVVAE_CONV_FORCE_DIRECT = 2, /* debugging: route cvvae_conv3d() to the CUDA-core kernel       */
+  CVVAE_CONV_OUT_F32 = 4       /* y holds fp32 (strides in fp32 elements); no residual, up_time 1  */
+};
+
+/* One strided channels-last 5-D tensor view. */
+typedef struct cvvae_tensor5 {
+  void* ptr;
+  int32_t B, T, H, W, C;
+  int64_t s_b, s_t, s_h, s_w, s_c; /* element strides */
+} cvvae_tensor5;
+
+/*
+ * Convolution (3-D, per-frame 2-D as KT=1, 1x1x1, strided, and plain GEMM as a 1x1x1 conv).
+ *
+ * Replaces, in the reference:
+ *   CausalConv3d.forward                models/vae_models.py:298-328, models/vae_blocks3d_sd3.py:81-104
+ *   nn.Conv3d / Conv3d(replicate)       models/vae_models.py:361,953,  models/vae_blocks3d_sd3.py:16-46
+ *   Conv2dWithExtraDim.forward          models/vae_models.py:331-340
+ *   Downsample3D.forward                models/vae_models.py:251-263,  models/vae_blocks3d_sd3.py:224-239
+ *   the conv + interleave of Upsample3D models/vae_models.py:229-232,  models/vae_blocks3d_sd3.py:352-362
+ *   nin_shortcut / conv_shortcut, q/k/v/proj_out 1x1 convs and the Linear layers of the attention blocks.
+ *
+ * y[b, to, ho, wo, co] = alpha * ( sum_{kt,kh,kw,ci} x[b, ti, hi, wi, ci] * w[(kt,kh,kw), co, ci] )
+ *                        + bias[co] + residual[b, to, ho, wo, co]
+ *   ti = to*st + kt + off_t   (pad_t: ZERO -> taps outside [0,T) contribute 0; REPLICATE -> clamp)
+ *   hi = ho*sh + kh + off_h, wi = wo*sw + kw + off_w  (pad_hw likewise)
+ * With up_time == 2 (Upsample3D, "b (n c) t h w -> b c (t n) h w" then drop frame 0): output channel
+ * co = n*(Cout/2) + c of conv-time t is stored at y[b, 2t+n-1, ho, wo, c] (dropped when 2t+n-1 < 0);
+ * y.C == Cout/2 and y.T == 2*T_conv-1 in that case.
+ * Weights are pre-packed by cvvae_pack_conv_weight(): [KT*KH*KW][Cout][Cin], Cin contiguous.
+ */
+typedef struct cvvae_conv_desc {
+  cvvae_tensor5 x;          /* input  */
+  cvvae_tensor5 y;          /* output (geometry after the optional time interleave) */
+  const void* w;            /* packed weights, activation dtype */
+  int64_t w_ld;             /* element stride between weight rows (0 -> Cin); multiple of 8 for the tc path */
+  const float* bias;        /* [Cout] (or [B*T*H*W] with CVVAE_CONV_BIAS_ALONG_M), may be NULL */
+  const void* residual;     /* same geometry/strides as y, may be NULL */
+  int32_t Cout;             /* conv output channels (before interleave) */
+  int32_t KT, KH, KW;
+  int32_t st, sh, sw;
+  int32_t off_t, off_h, off_w;
+  int32_t pad_t, pad_hw;    /* CVVAE_PAD_* */
+  int32_t up_time;          /* 1 or 2 */
+  int32_t dtype;            /* CVVAE_F16 / CVVAE_BF16 */
+  int32_t flags;            /* CVVAE_CONV_* */
+  float alpha;
+} cvvae_conv_desc;
+
+/* Dispatcher: tcgen05 implicit-GEMM kernel when eligible (x.s_c==1, Cin%8==0, 16B-aligned strides,
+ * pad_hw==ZERO), CUDA-core kernel otherwise (e.g. the 3/4-channel network inputs).              */
+int cvvae_conv3d(const cvvae_conv_desc* d, void* stream);
+int cvvae_conv3d_tc(const cvvae_conv_desc* d, void* stream);     /* tensor-core path only */
+int cvvae_conv3d_direct(const cvvae_conv_desc* d, void* stream); /* CUDA-core path only   */
+
+/* [Cout][Cin][KT][KH][KW] (PyTorch layout, contiguous, activation dtype) -> [KT*KH*KW][Cout][Cin]. */
+int cvvae_pack_conv_weight(const void* w_oikkk, void* w_packed, int32_t Cout, int32_t Cin, int32_t taps,
+                           int32_t dtype, void* stream);
+
+/*
+ * GroupNorm (+ optional SiLU), replacing Normalize()+nonlinearity (models/vae_models.py:187-195,
+ * 392-401) and nn.GroupNorm+nn.SiLU of the sd3 blocks.  Statistics over (C/groups, T, H, W) per
+ * sample; pass per_frame=1 for the attention blocks, whose GroupNorm sees T folded into the batch
+ * (models/vae_models.py:466,533,622).
+ *   stats workspace: fp64 [B*(per_frame?T:1)][groups][2]  (sum, sum of squares); zeroed by the call.
+ */
+int cvvae_groupnorm_stats(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats,
+                          int32_t dtype, void* stream);
+int cvvae_groupnorm_apply(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t groups, int32_t per_frame,
+                          const double* stats, const float* gamma, const float* beta, float eps,
+                          int32_t silu, int32_t dtype, void* stream);
+
+/* LayerNorm over C for every (b,t,h,w) token: norm_t of MemoryEfficientAttnVideoBlock
+ * (models/vae_models.py:571,575). */
+int cvvae_layernorm(const cvvae_tensor5* x, const cvvae_tensor5* y, const float* gamma, const float* beta,
+                    float eps, int32_t dtype, void* stream);
+
+/* Row softmax: fp32 logits s[rows][ld_s] -> 16-bit probabilities p[rows][ld_p] (first `cols` entries of
+ * each row), fp32 math.  Part of softmax(q k^T / sqrt(C)) v (models/vae_models.py:456,518,607). */
+int cvvae_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int64_t rows, int32_t cols,
+                       int32_t dtype, void* stream);
+
+/* Temporal attention of MemoryEfficientAttnVideoBlock.attention_t (models/vae_models.py:573-587):
+ * for every (b,h,w): tokens = the T frames, one head of dim C.  q,k,v,o are [B,T,H,W,C] views. */
+int cvvae_attn_temporal(const cvvae_tensor5* q, const cvvae_tensor5* k, const cvvae_tensor5* v,
+                        const cvvae_tensor5* o, int32_t dtype, void* stream);
+
+/* Nearest-neighbour x(1,2,2) upsample (F.interpolate in Upsample3D, models/vae_models.py:218-220). */
+int cvvae_upsample_nearest2x(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream);
+
+/* Replicate the outermost valid row/column of the interior [1,H-1)x[1,W-1) into the 1-pixel frame of
+ * a spatially pre-padded buffer (replicate padding of the sd3 convs, vae_blocks3d_sd3.py:87-98). */
+int cvvae_replicate_border(const cvvae_tensor5* xpad, int32_t dtype, void* stream);
+
+/* Generic strided copy / layout change between two 5-D views of equal logical shape. */
+int cvvae_copy5(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream);
+
+/* Tile blending, in place on b (models/modeling_vae.py:321-341):
+ *   b[..., i] = (1 - i/ov) * a[..., La-ov+i] + (i/ov) * b[..., i]   for i in [0,ov) along axis
+ * axis: 0 = width (blend_h), 1 = height (blend_v).  a and b are 5-D views with logical dims
+ * [B,T,H,W,C] (any strides, e.g. NCDHW tensors described with s_c = T*H*W). */
+int cvvae_blend(const cvvae_tensor5* a, const cvvae_tensor5* b, int32_t overlap, int32_t axis, int32_t dtype,
+                void* stream);
+
+/* Diagnostics */
+const char* cvvae_last_error(void);
+int cvvae_abi_version(void);
+/* Number of kernel launches issued through this library by the calling process (all threads). */
+int64_t cvvae_launch_count(void);
+/* Descriptor self-test used by the GPU test-suite: runs a 128xNx64 UMMA whose A operand starts
+ * `row_shift` 128-byte rows into a TMA-written SWIZZLE_128B slab, with the given base_offset field.
+ * out: fp32 [128][N].  (Decides how shifted conv taps may address one staged slab.) */
+int cvvae_probe_umma_shift(const void* a_rows, const void* b_rows, float* out, int32_t n, int32_t row_shift,
+                           int32_t base_offset_mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVVAE_B200_H_ */
