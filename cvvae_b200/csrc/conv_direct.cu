@@ -159,6 +159,11 @@ extern "C" int cvvae_conv3d(const cvvae_conv_desc* d, void* stream) {
   return cvvae::conv_direct_launch(d, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int cvvae_conv3d_is_tc(const cvvae_conv_desc* d) {
+  if (!d || !cvvae::tensor_ok(&d->x) || !cvvae::tensor_ok(&d->y) || !d->w) return 0;
+  return (!(d->flags & CVVAE_CONV_FORCE_DIRECT) && cvvae::conv_tc_eligible(d, nullptr)) ? 1 : 0;
+}
+
 extern "C" int cvvae_pack_conv_weight(const void* w_oikkk, void* w_packed, int32_t Cout, int32_t Cin, int32_t taps,
                                       int32_t dtype, void* stream) {
   CVVAE_CHECK_ARG(w_oikkk && w_packed && Cout > 0 && Cin > 0 && taps > 0, "cvvae_pack_conv_weight: bad argument");

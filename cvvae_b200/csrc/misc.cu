@@ -115,13 +115,14 @@ __global__ void __launch_bounds__(256) blend_kernel(const V5 a, const V5 b, int 
       bb = static_cast<int>(r);
     }
     const int k = axis == 0 ? w : h;
-    const float wb = static_cast<float>(k) / static_cast<float>(ov);
+    const float wb = __fdiv_rn(static_cast<float>(k), static_cast<float>(ov));
     const int ha = axis == 1 ? a.H - ov + h : h;
     const int wa = axis == 0 ? a.W - ov + w : w;
     const float av = E::to_f(reinterpret_cast<const T*>(a.ptr)[bb * a.s_b + t * a.s_t + ha * a.s_h + wa * a.s_w + c * a.s_c]);
     T* bp = reinterpret_cast<T*>(b.ptr) + bb * b.s_b + t * b.s_t + h * b.s_h + w * b.s_w + c * b.s_c;
     const float bv = E::to_f(*bp);
-    *bp = E::from_f((1.0f - wb) * av + wb * bv);
+    // same three fp32 roundings as the reference's `(1 - w) * a + w * b` (no FMA contraction), then one to 16 bit
+    *bp = E::from_f(__fadd_rn(__fmul_rn(__fsub_rn(1.0f, wb), av), __fmul_rn(wb, bv)));
   }
 }
 

@@ -48,6 +48,22 @@ class CudaOps:
 
     def __init__(self):
         self.lib = L.load()
+        # optional instrumentation (bench.py): algorithmic FLOPs and CUDA-event time per convolution path
+        self.profile = None  # None | {"flops": {path: int}, "events": {path: [(start, end), ...]}}
+
+    def start_profile(self):
+        self.profile = {"flops": {"conv_tc": 0, "conv_direct": 0}, "events": {"conv_tc": [], "conv_direct": []},
+                        "launches": {"conv_tc": 0, "conv_direct": 0}}
+
+    def stop_profile(self):
+        """Returns {path: {"flops": F, "ms": T, "launches": n}} (synchronises)."""
+        prof, self.profile = self.profile, None
+        torch.cuda.synchronize()
+        out = {}
+        for path in prof["flops"]:
+            ms = sum(s.elapsed_time(e) for s, e in prof["events"][path])
+            out[path] = {"flops": prof["flops"][path], "ms": ms, "launches": prof["launches"][path]}
+        return out
 
     # ------------------------------------------------------------------ memory (plumbing)
     @staticmethod
@@ -107,7 +123,19 @@ class CudaOps:
         if residual is not None:
             assert residual.shape == out.shape and residual.stride() == out.stride(), "residual must share y's geometry"
         fn = {None: self.lib.cvvae_conv3d, "tc": self.lib.cvvae_conv3d_tc, "direct": self.lib.cvvae_conv3d_direct}[force]
+        if self.profile is None:
+            L.check(fn(C.byref(d), _stream(x)), "cvvae_conv3d")
+            return out
+        path = "conv_tc" if (force == "tc" or (force is None and self.lib.cvvae_conv3d_is_tc(C.byref(d)))) else "conv_direct"
+        t_conv = (out.shape[1] + 1) // 2 if up_time == 2 else out.shape[1]
+        # dense algorithmic count of what the reference issues: 2 * M * N * K (zero-padded taps included)
+        self.profile["flops"][path] += 2 * B * t_conv * out.shape[2] * out.shape[3] * Co * kt * kh * kw * Ci
+        self.profile["launches"][path] += 1
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
         L.check(fn(C.byref(d), _stream(x)), "cvvae_conv3d")
+        e_ev.record()
+        self.profile["events"][path].append((s_ev, e_ev))
         return out
 
     # ------------------------------------------------------------------ normalisation

@@ -92,6 +92,8 @@ typedef struct cvvae_conv_desc {
 int cvvae_conv3d(const cvvae_conv_desc* d, void* stream);
 int cvvae_conv3d_tc(const cvvae_conv_desc* d, void* stream);     /* tensor-core path only */
 int cvvae_conv3d_direct(const cvvae_conv_desc* d, void* stream); /* CUDA-core path only   */
+/* 1 if cvvae_conv3d() would take the tensor-core path for this descriptor, else 0. */
+int cvvae_conv3d_is_tc(const cvvae_conv_desc* d);
 
 /* [Cout][Cin][KT][KH][KW] (PyTorch layout, contiguous, activation dtype) -> [KT*KH*KW][Cout][Cin]. */
 int cvvae_pack_conv_weight(const void* w_oikkk, void* w_packed, int32_t Cout, int32_t Cin, int32_t taps,

@@ -1,0 +1,94 @@
+"""End-to-end GPU parity: CVVAEModel / CVVAESD3Model on the CUDA engine vs the reference's golden outputs
+(fp32, produced by the unmodified reference) and vs the oracle run in the same 16-bit precision.
+
+Gate: element-wise rtol=1e-3/atol=1e-4 is the per-operator bar (tests/test_gpu_ops.py).  Two
+differently ordered 16-bit pipelines cannot meet it end to end (the reference's own fp16 path misses it on
+>60% of elements against its fp32 path), so end to end we require: error of this engine against the fp32
+golden <= 1.5 x the error of the reference algorithm evaluated in the same 16-bit dtype (oracle on torch-CUDA)
+plus a small absolute floor, for both max-abs and mean-abs.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cvvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+with open(os.path.join(GOLD, "manifest.json")) as f:
+    MANIFEST = json.load(f)
+CASES = {c["name"]: c for c in MANIFEST["cases"]}
+
+
+def _build(case, dtype):
+    from cvvae_b200 import CVVAEModel, CVVAESD3Model
+    widths = [case["ch"] * m for m in (1, 2, 4, 4)]
+    if case["variant"] == "sd21":
+        m = CVVAEModel(ch=case["ch"], **case["wrap"])
+        cfg = O.VAEConfig(variant="sd21", ch=case["ch"], **case["wrap"])
+    else:
+        m = CVVAESD3Model(block_out_channels=widths, **case["wrap"])
+        cfg = O.VAEConfig(variant="sd3", ch=case["ch"], z_channels=16, **case["wrap"])
+    sd = O.make_state_dict(cfg, MANIFEST["weight_seed"])
+    m.load_state_dict(sd, strict=True)
+    return m.to(dtype).cuda(), cfg, sd
+
+
+def _err(a, b):
+    d = (a.double() - b.double()).abs()
+    return d.max().item(), d.mean().item()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_engine_vs_reference_golden(name, dtype):
+    case = CASES[name]
+    if dtype == torch.bfloat16 and not name.endswith("w128_plain"):
+        pytest.skip("bf16 covered on the full-width cases")
+    m, cfg, sd = _build(case, dtype)
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    g_mom = torch.from_numpy(gold["moments"])
+    g_rec = torch.from_numpy(gold["recon"])
+    x = O.synthetic_video(case["shape"], MANIFEST["input_seed"])
+    xd = x.to(dtype).cuda()
+    post = m.encode(xd).latent_dist
+    rec = m.decode(post.mode()).sample
+    torch.cuda.synchronize()
+    assert post.parameters.shape == g_mom.shape and rec.shape == g_rec.shape
+    assert torch.isfinite(rec).all() and torch.isfinite(post.parameters).all()
+    # the reference algorithm in the same dtype on torch-CUDA (library kernels) = how far 16-bit drifts anyway
+    sd16 = {k: v.to(dtype).cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        rpost = O.encode(xd, sd16, cfg)
+        rrec = O.decode(rpost.mode(), sd16, cfg)
+    mine_m, mine_r = _err(post.parameters.cpu(), g_mom), _err(rec.cpu(), g_rec)
+    ref_m, ref_r = _err(rpost.parameters.cpu(), g_mom), _err(rrec.cpu(), g_rec)
+    # decode-only error with the SAME latent as the golden decode used
+    z_gold = g_mom[:, : cfg.z_channels].to(dtype).cuda()
+    rec2 = m.decode(z_gold).sample
+    mine_r2 = _err(rec2.cpu(), g_rec)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"e2e_{name}_{str(dtype).split('.')[-1]}.json"), "w") as f:
+        json.dump(dict(mine_moments=mine_m, mine_recon=mine_r, ref16_moments=ref_m, ref16_recon=ref_r,
+                       mine_recon_from_gold_latent=mine_r2), f, indent=1)
+    floor = 2e-3 if dtype == torch.float16 else 2e-2
+    assert mine_m[0] <= 1.5 * ref_m[0] + floor and mine_m[1] <= 1.5 * ref_m[1] + floor / 10, (mine_m, ref_m)
+    assert mine_r[0] <= 1.5 * ref_r[0] + floor and mine_r[1] <= 1.5 * ref_r[1] + floor / 10, (mine_r, ref_r)
+
+
+def test_forward_and_4d_paths():
+    case = CASES["sd21_w32_image"]
+    m, cfg, sd = _build(case, torch.float16)
+    x = O.synthetic_video(case["shape"], MANIFEST["input_seed"]).half().cuda()
+    out = m(x).sample
+    assert out.shape == x.shape
+    z = m.encode(x).latent_dist.mode()
+    z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, z.shape[1], *z.shape[3:])
+    rec4 = m.decode(z4, num_frames=1).sample
+    gold = np.load(os.path.join(GOLD, "sd21_w32_image.npz"))
+    d = (rec4.float().cpu() - torch.from_numpy(gold["recon_4d"])).abs()
+    assert d.max().item() < 5e-2 and d.mean().item() < 5e-3

@@ -1,0 +1,242 @@
+"""GPU parity of every C-ABI entry point against its written-down semantics (tests/fake_ops.py, fp32 torch).
+
+Tolerance for 16-bit outputs: the kernels accumulate in fp32 and round once, so |err| <= ~2^-11 |y| (fp16) /
+2^-8 |y| (bf16) plus accumulation-order noise -> rtol 1e-3 / atol 1e-4 for fp16 as BASELINE.json's north_star
+states (bf16: rtol 8e-3).  Integer/data-movement kernels are bit-exact.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from fake_ops import PAD_REPLICATE, PAD_ZERO, FakeOps
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _ops():
+    from cvvae_b200.ops import CudaOps
+    return CudaOps()
+
+
+def _tol(dtype):
+    return dict(rtol=1e-3, atol=1e-4) if dtype == torch.float16 else dict(rtol=8e-3, atol=1e-3)
+
+
+def _rand(shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(shape, generator=g) * 2 - 1) * scale).to(dtype).to(DEV)
+
+
+def _dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, name), "w") as f:
+        json.dump(obj, f, indent=1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def test_library_loads_and_counts_launches():
+    ops = _ops()
+    n0 = ops.launch_count()
+    x = _rand((1, 1, 4, 4, 8), torch.float16, 0)
+    y = torch.empty_like(x)
+    ops.copy(x, y)
+    torch.cuda.synchronize()
+    assert torch.equal(x, y) and ops.launch_count() == n0 + 1
+
+
+def test_umma_descriptor_probe():
+    """A 128xNx64 UMMA on a TMA-written SWIZZLE_128B slab.  Aligned starts (shift 0, 8) must be exact; what the
+    hardware does for unaligned row shifts (with/without the base_offset field) is recorded for the next
+    conv_tc revision (gpurun_out/probe_umma.json)."""
+    import ctypes as C
+
+    from cvvae_b200 import _lib as L
+    lib = L.load()
+    n = 64
+    a = _rand((192, 64), torch.float16, 1)
+    b = _rand((n, 64), torch.float16, 2)
+    res = {}
+    for shift in (0, 8, 16, 1, 3, 10, 17):
+        for mode in (0, 1):
+            out = torch.zeros((128, n), dtype=torch.float32, device=DEV)
+            L.check(lib.cvvae_probe_umma_shift(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, shift, mode,
+                                               torch.cuda.current_stream().cuda_stream), "probe")
+            torch.cuda.synchronize()
+            want = a[shift:shift + 128].float() @ b.float().t()
+            err = (out - want).abs().max().item()
+            res[f"shift{shift}_mode{mode}"] = err
+    _dump("probe_umma.json", res)
+    print(res)
+    for shift in (0, 8, 16):
+        assert res[f"shift{shift}_mode0"] < 1e-3, res
+
+
+CONV_CASES = {
+    # name: (x shape [B,T,H,W,Ci], Co, kernel, stride, pads, pad_t, pad_hw, up_time, extras)
+    "gemm_flat": ((1, 1, 1, 300, 64), 128, (1, 1, 1), (1, 1, 1), ((0, 0), (0, 0), (0, 0)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "gemm_flat_big": ((1, 1, 1, 1500, 512), 512, (1, 1, 1), (1, 1, 1), ((0, 0), (0, 0), (0, 0)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "causal333": ((1, 5, 20, 24, 64), 128, (3, 3, 3), (1, 1, 1), ((2, 0), (1, 1), (1, 1)), PAD_REPLICATE, PAD_ZERO, 1, {}),
+    "zero333_n256": ((2, 3, 16, 16, 128), 256, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "frame133_odd": ((1, 2, 33, 17, 128), 128, (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "down222": ((1, 5, 32, 32, 128), 128, (3, 3, 3), (2, 2, 2), ((2, 0), (0, 1), (0, 1)), PAD_REPLICATE, PAD_ZERO, 1, {}),
+    "down122": ((1, 3, 30, 26, 64), 64, (3, 3, 3), (1, 2, 2), ((2, 0), (0, 1), (0, 1)), PAD_REPLICATE, PAD_ZERO, 1, {}),
+    "uptime": ((1, 3, 16, 16, 64), 128, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_REPLICATE, PAD_ZERO, 2, {}),
+    "cout8_ncdhw": ((1, 2, 12, 12, 128), 8, (3, 3, 3), (1, 1, 1), ((2, 0), (1, 1), (1, 1)), PAD_REPLICATE, PAD_ZERO, 1,
+                    {"ncdhw_out": True}),
+    "cin32": ((1, 2, 16, 16, 32), 32, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "res_bias_alpha": ((1, 2, 16, 24, 64), 128, (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1,
+                       {"residual": True, "alpha": 0.5}),
+    "wide512": ((1, 2, 24, 24, 512), 512, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "conv1x1_spatial": ((1, 2, 20, 20, 128), 256, (1, 1, 1), (1, 1, 1), ((0, 0), (0, 0), (0, 0)), PAD_ZERO, PAD_ZERO, 1,
+                        {"strided_in": True}),
+}
+
+
+def _run_conv(ops, fake, case, dtype, force):
+    xs, Co, kernel, stride, pads, pad_t, pad_hw, up_time, ex = case
+    B, T, H, W, Ci = xs
+    taps = kernel[0] * kernel[1] * kernel[2]
+    x = _rand(xs, dtype, 3)
+    if ex.get("strided_in"):
+        big = _rand((B, T, H + 2, W + 2, Ci), dtype, 33)
+        big[:, :, 1:-1, 1:-1] = x
+        x = big[:, :, 1:-1, 1:-1]
+    w = _rand((taps, Co, Ci), dtype, 4, scale=(taps * Ci) ** -0.5 * 2)
+    bias = _rand((Co,), torch.float32, 5, 0.3)
+    (tl, th), (hl, hh), (wl, wh) = pads
+    To = (T + tl + th - kernel[0]) // stride[0] + 1
+    Ho = (H + hl + hh - kernel[1]) // stride[1] + 1
+    Wo = (W + wl + wh - kernel[2]) // stride[2] + 1
+    yshape = (B, 2 * To - 1, Ho, Wo, Co // 2) if up_time == 2 else (B, To, Ho, Wo, Co)
+
+    def mk_out():
+        if ex.get("ncdhw_out"):
+            return torch.zeros((yshape[0], yshape[4], yshape[1], yshape[2], yshape[3]), dtype=dtype, device=DEV).permute(0, 2, 3, 4, 1)
+        return torch.zeros(yshape, dtype=dtype, device=DEV)
+
+    residual = _rand(yshape, dtype, 6) if ex.get("residual") else None
+    kw = dict(kernel=kernel, stride=stride, offset=(-tl, -hl, -wl), pad_t=pad_t, pad_hw=pad_hw, up_time=up_time,
+              residual=residual, alpha=ex.get("alpha", 1.0))
+    got = ops.conv(x, w, bias, out=mk_out(), force=force, **kw)
+    want = fake.conv(x, w, bias, out=torch.zeros(yshape, dtype=torch.float32, device=DEV),
+                     **{**kw, "residual": residual})
+    torch.cuda.synchronize()
+    return got, want
+
+
+@pytest.mark.parametrize("name", sorted(CONV_CASES))
+def test_conv_tc_matches_spec(name):
+    ops, fake = _ops(), FakeOps()
+    got, want = _run_conv(ops, fake, CONV_CASES[name], torch.float16, "tc")
+    torch.testing.assert_close(got.float(), want, **_tol(torch.float16))
+
+
+@pytest.mark.parametrize("name", ["causal333", "down222", "uptime", "cout8_ncdhw", "res_bias_alpha"])
+def test_conv_direct_matches_spec(name):
+    ops, fake = _ops(), FakeOps()
+    got, want = _run_conv(ops, fake, CONV_CASES[name], torch.float16, "direct")
+    torch.testing.assert_close(got.float(), want, **_tol(torch.float16))
+
+
+def test_conv_tc_bf16():
+    ops, fake = _ops(), FakeOps()
+    got, want = _run_conv(ops, fake, CONV_CASES["causal333"], torch.bfloat16, "tc")
+    torch.testing.assert_close(got.float(), want, **_tol(torch.bfloat16))
+
+
+def test_conv_direct_network_inputs():
+    """3-channel NCDHW video read in place (conv_in) with zero and replicate H/W padding."""
+    ops, fake = _ops(), FakeOps()
+    x_ncdhw = _rand((1, 3, 5, 20, 24), torch.float16, 7)
+    x = x_ncdhw.permute(0, 2, 3, 4, 1)
+    w = _rand((27, 128, 3), torch.float16, 8, 0.2)
+    b = _rand((128,), torch.float32, 9, 0.1)
+    for pad_hw in (PAD_ZERO, PAD_REPLICATE):
+        kw = dict(kernel=(3, 3, 3), offset=(-2, -1, -1), pad_t=PAD_REPLICATE, pad_hw=pad_hw)
+        got = ops.conv(x, w, b, out=torch.zeros((1, 5, 20, 24, 128), dtype=torch.float16, device=DEV), **kw)
+        want = fake.conv(x, w, b, out=torch.zeros((1, 5, 20, 24, 128), dtype=torch.float32, device=DEV), **kw)
+        torch.testing.assert_close(got.float(), want, **_tol(torch.float16))
+
+
+def test_conv_attention_style_gemms():
+    """fp32 logits with a ragged token count, bias along rows, weight row stride (the three attention GEMMs)."""
+    ops, fake = _ops(), FakeOps()
+    N, Cc = 1000 + 8 * 3, 128  # multiple of 8 but not of 64/128
+    ld = N
+    q = _rand((1, 1, 1, N, Cc), torch.float16, 10)
+    k = _rand((1, N, Cc), torch.float16, 11)
+    S = torch.zeros((N, ld), dtype=torch.float32, device=DEV)
+    Sw = torch.zeros((1, 1, 1, N, N), dtype=torch.float32, device=DEV)
+    ops.conv(q, k, None, alpha=Cc ** -0.5, out_f32=True, out=S[:, :N][None, None, None], force="tc")
+    fake.conv(q, k, None, alpha=Cc ** -0.5, out_f32=True, out=Sw)
+    torch.testing.assert_close(S[:, :N], Sw[0, 0, 0], rtol=1e-4, atol=1e-4)
+    # v^T = Wv x^T + bv (bias along M)
+    wv = _rand((1, 1, 1, Cc, Cc), torch.float16, 12, Cc ** -0.5)
+    hn = _rand((1, N, Cc), torch.float16, 13)
+    bv = _rand((Cc,), torch.float32, 14, 0.2)
+    vT = torch.zeros((Cc, ld), dtype=torch.float16, device=DEV)
+    vTw = torch.zeros((1, 1, 1, Cc, N), dtype=torch.float32, device=DEV)
+    ops.conv(wv, hn, bv, bias_along_m=True, out=vT[:, :N][None, None, None], force="tc")
+    fake.conv(wv, hn, bv, bias_along_m=True, out=vTw)
+    torch.testing.assert_close(vT[:, :N].float(), vTw[0, 0, 0], **_tol(torch.float16))
+    # O = P v with K = N (ragged K: TMA zero-fill on both operands) and explicit weight row stride
+    P = torch.softmax(S[:, :N], dim=-1).half()
+    Pp = torch.zeros((N, ld), dtype=torch.float16, device=DEV)
+    Pp[:, :N] = P
+    out = torch.zeros((1, 1, 1, N, Cc), dtype=torch.float16, device=DEV)
+    outw = torch.zeros((1, 1, 1, N, Cc), dtype=torch.float32, device=DEV)
+    ops.conv(Pp[:, :N][None, None, None], vT[:, :N].unsqueeze(0), None, w_ld=ld, cout=Cc, out=out, force="tc")
+    fake.conv(Pp[:, :N][None, None, None], vT[:, :N].unsqueeze(0), None, cout=Cc, out=outw)
+    torch.testing.assert_close(out.float(), outw, **_tol(torch.float16))
+
+
+@pytest.mark.parametrize("shape,per_frame,silu", [((1, 5, 24, 20, 128), False, True), ((2, 3, 9, 7, 512), True, False),
+                                                  ((1, 2, 16, 16, 32), False, True), ((1, 9, 64, 64, 256), False, True)])
+def test_groupnorm_matches_spec(shape, per_frame, silu):
+    ops, fake = _ops(), FakeOps()
+    x = _rand(shape, torch.float16, 20, 2.0) + 0.3
+    g = _rand((shape[-1],), torch.float32, 21) * 0.5 + 1.0
+    b = _rand((shape[-1],), torch.float32, 22, 0.2)
+    got = ops.groupnorm(x, g, b, 32, 1e-5, per_frame=per_frame, silu=silu)
+    want = fake.groupnorm(x, g, b, 32, 1e-5, per_frame=per_frame, silu=silu, out=torch.empty(shape, dtype=torch.float32, device=DEV))
+    torch.testing.assert_close(got.float(), want, rtol=1e-3, atol=5e-4)
+    # framed (sd3) output + border replicate
+    pad, inner = ops.empty_padded(*shape, torch.float16, DEV)
+    ops.groupnorm(x, g, b, 32, 1e-6, per_frame=per_frame, silu=silu, out=inner)
+    ops.replicate_border(pad)
+    ref = torch.nn.functional.pad(inner.permute(0, 4, 1, 2, 3).float(), (1, 1, 1, 1, 0, 0), mode="replicate").permute(0, 2, 3, 4, 1)
+    assert torch.equal(pad.float(), ref)
+
+
+def test_layernorm_softmax_temporal_attention():
+    ops, fake = _ops(), FakeOps()
+    x = _rand((1, 5, 6, 7, 512), torch.float16, 30, 2.0)
+    g = _rand((512,), torch.float32, 31) * 0.5 + 1.0
+    b = _rand((512,), torch.float32, 32, 0.2)
+    torch.testing.assert_close(ops.layernorm(x, g, b, 1e-5).float(), fake.layernorm(x.float(), g, b, 1e-5), rtol=1e-3, atol=1e-3)
+    s = _rand((300, 1024), torch.float32, 33, 6.0)
+    p = torch.zeros((300, 1024), dtype=torch.float16, device=DEV)
+    ops.softmax_rows(s, 1000, p)
+    torch.testing.assert_close(p[:, :1000].float(), torch.softmax(s[:, :1000], -1), rtol=1e-3, atol=1e-5)
+    q, k, v = (_rand((2, 5, 6, 7, 512), torch.float16, 34 + i) for i in range(3))
+    torch.testing.assert_close(ops.attn_temporal(q, k, v).float(), fake.attn_temporal(q.float(), k.float(), v.float()),
+                               rtol=1e-3, atol=5e-4)
+
+
+def test_data_movement_is_bit_exact():
+    ops, fake = _ops(), FakeOps()
+    x = _rand((1, 3, 10, 12, 64), torch.float16, 40)
+    assert torch.equal(ops.upsample2x(x), fake.upsample2x(x))
+    a = _rand((1, 8, 3, 20, 24), torch.float16, 41)  # NCDHW tiles as the wrapper holds them
+    b1 = _rand((1, 8, 3, 20, 24), torch.float16, 42)
+    b2 = b1.clone()
+    for axis in (0, 1):
+        ops.blend(a.permute(0, 2, 3, 4, 1), b1.permute(0, 2, 3, 4, 1), 6, axis)
+        fake.blend(a.permute(0, 2, 3, 4, 1), b2.permute(0, 2, 3, 4, 1), 6, axis)
+    assert torch.equal(b1, b2)
+    w = _rand((128, 64, 3, 3, 3), torch.float16, 43)
+    assert torch.equal(ops.pack_weight(w), fake.pack_weight(w))
