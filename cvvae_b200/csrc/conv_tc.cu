@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t sub_stride = p.flat ? 16384u : static_cast<uint32_t>(p.ROWS * p.TW) * 128u;
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&fullA[slotA], phaseA);
+        // K = 16 per MMA; channels beyond Cin are TMA zero-fill in both operands, skip those MMAs entirely
+        const int ch_left = p.Cin - cb * 64;
+        const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
         const uint32_t a_slot = ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes);
         for (int khs = 0; khs < p.KHs; ++khs) {
           wait_bar(&fullB[slotB], phaseB);
@@ -193,8 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int s = 0; s < nacc_eff; ++s) {
             const uint32_t a_sub = a_tap + s * sub_stride;
             const uint32_t d = tmem_base + static_cast<uint32_t>(s * p.N_cta);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < ksteps; ++k) {
               ptx::umma_f16(d, ptx::umma_desc_k_sw128(a_sub + k * 32, 1024), ptx::umma_desc_k_sw128(b_slot + k * 32, 1024),
                             p.idesc, accumulate | static_cast<uint32_t>(k));
             }

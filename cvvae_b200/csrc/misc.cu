@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) copy5_kernel(const V5 x, const V5 y) {
       b = static_cast<int>(r);
     }
     reinterpret_cast<uint16_t*>(y.ptr)[b * y.s_b + t * y.s_t + h * y.s_h + w * y.s_w + c * y.s_c] =
-        reinterpret_cast<const uint16_t*>(x.ptr)[b * x.s_b + t * x.s_t + h * x.s_h + w * x.s_w + c * x.s_c];
+        c < x.C ? reinterpret_cast<const uint16_t*>(x.ptr)[b * x.s_b + t * x.s_t + h * x.s_h + w * x.s_w + c * x.s_c]
+                : static_cast<uint16_t>(0);  // channel zero-fill when the destination is wider
   }
 }
 
@@ -163,7 +164,7 @@ extern "C" int cvvae_replicate_border(const cvvae_tensor5* xpad, int32_t dtype, 
 extern "C" int cvvae_copy5(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream) {
   (void)dtype;
   CVVAE_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "cvvae_copy5: null argument");
-  CVVAE_CHECK_ARG(y->B == x->B && y->T == x->T && y->H == x->H && y->W == x->W && y->C == x->C, "cvvae_copy5: shape mismatch");
+  CVVAE_CHECK_ARG(y->B == x->B && y->T == x->T && y->H == x->H && y->W == x->W && y->C >= x->C, "cvvae_copy5: shape mismatch");
   const long long n = 1ll * y->B * y->T * y->H * y->W * y->C;
   copy5_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(x), mk(y));
   CVVAE_LAUNCH_CHECK();

@@ -66,7 +66,14 @@ def prepack_params(state_dict: Dict[str, torch.Tensor], ops, dtype: torch.dtype)
     packed = {}
     for k, v in state_dict.items():
         if k.endswith(".weight") and v.dim() >= 2:
-            packed[k] = ops.pack_weight(v.detach().to(dtype))
+            v = v.detach().to(dtype)
+            if k in ("encoder.conv_in.weight", "decoder.conv_in.weight") and v.shape[1] % 8:
+                # network inputs have 3 / 4 channels: zero-pad Cin to 8 so the channel-padded channels-last copy of the
+                # input (Engine.conv) runs on the tensor-core path; the MMA loop skips the all-zero K steps
+                vp = torch.zeros((v.shape[0], (v.shape[1] + 7) // 8 * 8) + tuple(v.shape[2:]), dtype=dtype, device=v.device)
+                vp[:, : v.shape[1]] = v
+                v = vp
+            packed[k] = ops.pack_weight(v)
         else:
             packed[k] = v.detach().to(torch.float32).contiguous()
     return packed
@@ -122,6 +129,18 @@ class Engine:
             assert tuple(out.shape) == yshape, (tuple(out.shape), yshape)
         off = (-tl, -hl, -wl)
         needs_hw_pad = (kh > 1 or kw > 1) and (hl or hh or wl or wh)
+        if not self._tc_ok(x):
+            # the caller's NCDHW tensor (network input, 3 / 4 / 16 channels): one gather into a channels-last,
+            # channel-padded buffer (framed when the conv wants replicate padding) feeds the tensor-core path
+            Cp = w.shape[2]
+            if pad_hw == PAD_REPLICATE and needs_hw_pad:
+                pad, inner = self.ops.empty_padded(B, T, H, W, Cp, x.dtype, x.device)
+                self.ops.copy(x, inner)
+                self.ops.replicate_border(pad)
+                a = Act(inner, pad)
+            else:
+                a = Act(self.ops.copy(x, self.ops.empty((B, T, H, W, Cp), x.dtype, x.device)))
+            x = a.t
         if pad_hw == PAD_REPLICATE and needs_hw_pad and self._tc_ok(x):
             a = self._framed(a)
             x = a.pad

@@ -134,7 +134,8 @@ int cvvae_upsample_nearest2x(const cvvae_tensor5* x, const cvvae_tensor5* y, int
  * a spatially pre-padded buffer (replicate padding of the sd3 convs, vae_blocks3d_sd3.py:87-98). */
 int cvvae_replicate_border(const cvvae_tensor5* xpad, int32_t dtype, void* stream);
 
-/* Generic strided copy / layout change between two 5-D views of equal logical shape. */
+/* Generic strided copy / layout change between two 5-D views of equal logical shape; y may have more
+ * channels than x, the extra channels are zero-filled (channel padding of the 3/4-channel network inputs). */
 int cvvae_copy5(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream);
 
 /* Tile blending, in place on b (models/modeling_vae.py:321-341):

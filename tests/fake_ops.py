@@ -156,17 +156,20 @@ class FakeOps:
 
     def copy(self, x, out):
         self.launches += 1
-        out.copy_(x)
+        c = x.shape[-1]
+        out[..., :c] = x
+        if out.shape[-1] > c:
+            out[..., c:] = 0
         return out
 
     def blend(self, a, b, overlap, axis):
         self.launches += 1
         ov = overlap
         if axis == 0:
-            wgt = (torch.arange(ov, device=b.device) / ov).view(1, 1, 1, -1, 1)
+            wgt = (torch.arange(ov) / ov).view(1, 1, 1, -1, 1).to(b.device)  # CPU division, as the reference
             b[:, :, :, :ov] = ((1 - wgt) * a[:, :, :, -ov:] + wgt * b[:, :, :, :ov]).to(b.dtype)
         else:
-            wgt = (torch.arange(ov, device=b.device) / ov).view(1, 1, -1, 1, 1)
+            wgt = (torch.arange(ov) / ov).view(1, 1, -1, 1, 1).to(b.device)
             b[:, :, :ov] = ((1 - wgt) * a[:, :, -ov:] + wgt * b[:, :, :ov]).to(b.dtype)
         return b
 
