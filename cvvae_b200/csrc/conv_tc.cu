@@ -136,21 +136,26 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------- A producer
-    if (lane == 0) {
+    // The whole warp walks the step sequence (so every operand the TMA instruction takes is provably
+    // warp-uniform and lives in uniform registers); one elected lane issues.
+    {
       int slot = 0;
       uint32_t phase = 0;
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&emptyA[slot], phase ^ 1);
         uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_bytes;
-        if (p.flat) {
-          ptx::mbar_expect_tx(&fullA[slot], static_cast<uint32_t>(nacc_eff) * 128u * 128u);
-          for (int s = 0; s < nacc_eff; ++s)
-            ptx::tma_load_5d(dst + s * 16384, &tmA, &fullA[slot], cb * 64, tc.w0 + s * 128, 0, ti, tc.b);
-        } else {
-          ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
-          ptx::tma_load_5d(dst, &tmA, &fullA[slot], cb * 64, tc.w0 * p.sw + kw + p.off_w,
-                           tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
+        if (ptx::elect_one()) {
+          if (p.flat) {
+            ptx::mbar_expect_tx(&fullA[slot], static_cast<uint32_t>(nacc_eff) * 128u * 128u);
+            for (int s = 0; s < nacc_eff; ++s)
+              ptx::tma_load_5d(dst + s * 16384, &tmA, &fullA[slot], cb * 64, tc.w0 + s * 128, 0, ti, tc.b);
+          } else {
+            ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
+            ptx::tma_load_5d(dst, &tmA, &fullA[slot], cb * 64, tc.w0 * p.sw + kw + p.off_w,
+                             tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
+          }
         }
+        __syncwarp();
         if (++slot == p.NA) {
           slot = 0;
           phase ^= 1;
@@ -159,15 +164,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- B producer
-    if (lane == 0) {
+    {
       int slot = 0;
       uint32_t phase = 0;
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         for (int khs = 0; khs < p.KHs; ++khs) {
           const int tap = (kt * p.KH + hg * p.KHs + khs) * p.KW + kw;
           wait_bar(&emptyB[slot], phase ^ 1);
-          ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
-          ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+            ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
+          }
+          __syncwarp();
           if (++slot == p.NB) {
             slot = 0;
             phase ^= 1;
@@ -177,44 +185,64 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // Issue rate matters: one UTCHMMA covers only 64 (N=128) / 128 (N=256) tensor-pipe cycles, so the loop
+    // around it must stay a handful of uniform-datapath instructions.  All 32 lanes run the control flow
+    // (operands provably uniform -> no per-instruction ELECT/broadcast sequences), descriptors are a
+    // precomputed 64-bit base whose low word advances by constants, and only the elected lane issues.
+    {
       int slotA = 0, slotB = 0;
       uint32_t phaseA = 0, phaseB = 0;
       uint32_t accumulate = 0;
-      const uint32_t sub_stride = p.flat ? 16384u : static_cast<uint32_t>(p.ROWS * p.TW) * 128u;
+      const uint32_t sub_stride16 = (p.flat ? 16384u : static_cast<uint32_t>(p.ROWS * p.TW) * 128u) >> 4;
+      const uint32_t tap_stride16 = (static_cast<uint32_t>(p.TW) * 128u) >> 4;
+      const uint32_t idesc = p.idesc;
+      const uint32_t ncta = static_cast<uint32_t>(p.N_cta);
+      // descriptor high word: SBO = 1024 B (>>4 = 64) at [32,46), version 1 at [46,48), SWIZZLE_128B at [61,64)
+      constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+      constexpr uint32_t kDescLoFlags = 1u << 16;  // LBO field (canonical 1 for swizzled K-major)
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&fullA[slotA], phaseA);
         // K = 16 per MMA; channels beyond Cin are TMA zero-fill in both operands, skip those MMAs entirely
         const int ch_left = p.Cin - cb * 64;
         const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
-        const uint32_t a_slot = ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes);
+        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
         for (int khs = 0; khs < p.KHs; ++khs) {
           wait_bar(&fullB[slotB], phaseB);
           ptx::tc_fence_after();
-          const uint32_t b_slot = ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes);
-          const uint32_t a_tap = a_slot + static_cast<uint32_t>(khs * p.TW) * 128u;
-          for (int s = 0; s < nacc_eff; ++s) {
-            const uint32_t a_sub = a_tap + s * sub_stride;
-            const uint32_t d = tmem_base + static_cast<uint32_t>(s * p.N_cta);
-            for (int k = 0; k < ksteps; ++k) {
-              ptx::umma_f16(d, ptx::umma_desc_k_sw128(a_sub + k * 32, 1024), ptx::umma_desc_k_sw128(b_slot + k * 32, 1024),
-                            p.idesc, accumulate | static_cast<uint32_t>(k));
+          const uint32_t b_lo0 = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+          const uint32_t a_lo1 = a_lo0 + static_cast<uint32_t>(khs) * tap_stride16;
+          if (ptx::elect_one()) {
+            for (int s = 0; s < nacc_eff; ++s) {
+              const uint32_t a_lo = a_lo1 + static_cast<uint32_t>(s) * sub_stride16;
+              const uint32_t d = tmem_base + static_cast<uint32_t>(s) * ncta;
+              if (ksteps == 4) {
+                ptx::umma_f16_lohi(d, a_lo, b_lo0, kDescHi, idesc, accumulate);
+                ptx::umma_f16_lohi(d, a_lo + 2, b_lo0 + 2, kDescHi, idesc, 1);
+                ptx::umma_f16_lohi(d, a_lo + 4, b_lo0 + 4, kDescHi, idesc, 1);
+                ptx::umma_f16_lohi(d, a_lo + 6, b_lo0 + 6, kDescHi, idesc, 1);
+              } else {
+                for (int k = 0; k < ksteps; ++k)
+                  ptx::umma_f16_lohi(d, a_lo + 2 * k, b_lo0 + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+              }
             }
+            ptx::umma_commit(&emptyB[slotB]);
           }
+          __syncwarp();
           accumulate = 1;
-          ptx::umma_commit(&emptyB[slotB]);
           if (++slotB == p.NB) {
             slotB = 0;
             phaseB ^= 1;
           }
         }
-        ptx::umma_commit(&emptyA[slotA]);
+        if (ptx::elect_one()) ptx::umma_commit(&emptyA[slotA]);
+        __syncwarp();
         if (++slotA == p.NA) {
           slotA = 0;
           phaseA ^= 1;
         }
       });
-      ptx::umma_commit(accFull);
+      if (ptx::elect_one()) ptx::umma_commit(accFull);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------- epilogue

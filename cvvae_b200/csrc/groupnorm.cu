@@ -59,7 +59,31 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnView v, double* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (pl < lanes) {
-    for (long long p = p0 + pl; p < p1; p += lanes) {
+    // 4 independent 128-bit loads in flight per thread (HBM latency x bandwidth needs ~35 KB in flight per SM)
+    constexpr int U = 4;
+    long long p = p0 + pl;
+    for (; p + static_cast<long long>(U - 1) * lanes < p1; p += static_cast<long long>(U) * lanes) {
+      uint4 u[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const long long off = gn_offset(p + static_cast<long long>(i) * lanes, ut, v.per_frame, v.H, v.W, v.xs_t, v.xs_h,
+                                        v.xs_w, v.x_dense, v.C);
+        u[i] = __ldg(reinterpret_cast<const uint4*>(xb + off + vec * 8));
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const uint32_t uw[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = E::to_f2(uw[j]);
+          s[2 * j] += f.x;
+          q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+          s[2 * j + 1] += f.y;
+          q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+        }
+      }
+    }
+    for (; p < p1; p += lanes) {
       const long long off = gn_offset(p, ut, v.per_frame, v.H, v.W, v.xs_t, v.xs_h, v.xs_w, v.x_dense, v.C);
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + off + vec * 8));
       const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
@@ -146,10 +170,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const dou
   if (p1 > v.pix_per_unit) p1 = v.pix_per_unit;
   const typename E::T* xb = reinterpret_cast<const typename E::T*>(v.x) + b * v.xs_b;
   typename E::T* yb = reinterpret_cast<typename E::T*>(v.y) + b * v.ys_b;
-  for (long long p = p0 + pl; p < p1; p += lanes) {
-    const long long xo = gn_offset(p, ut, v.per_frame, v.H, v.W, v.xs_t, v.xs_h, v.xs_w, v.x_dense, v.C);
-    const long long yo = gn_offset(p, ut, v.per_frame, v.H, v.W, v.ys_t, v.ys_h, v.ys_w, v.y_dense, v.C);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + xo + vec * 8));
+  auto transform = [&](const uint4& u) {
     const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
     uint32_t ow[4];
 #pragma unroll
@@ -163,7 +184,27 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const dou
       }
       ow[j] = E::pack2(r0, r1);
     }
-    *reinterpret_cast<uint4*>(yb + yo + vec * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  };
+  constexpr int U = 4;  // independent 128-bit loads in flight per thread
+  long long p = p0 + pl;
+  for (; p + static_cast<long long>(U - 1) * lanes < p1; p += static_cast<long long>(U) * lanes) {
+    uint4 u[U];
+    long long yo[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const long long pp = p + static_cast<long long>(i) * lanes;
+      const long long xo = gn_offset(pp, ut, v.per_frame, v.H, v.W, v.xs_t, v.xs_h, v.xs_w, v.x_dense, v.C);
+      yo[i] = gn_offset(pp, ut, v.per_frame, v.H, v.W, v.ys_t, v.ys_h, v.ys_w, v.y_dense, v.C);
+      u[i] = __ldg(reinterpret_cast<const uint4*>(xb + xo + vec * 8));
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) *reinterpret_cast<uint4*>(yb + yo[i] + vec * 8) = transform(u[i]);
+  }
+  for (; p < p1; p += lanes) {
+    const long long xo = gn_offset(p, ut, v.per_frame, v.H, v.W, v.xs_t, v.xs_h, v.xs_w, v.x_dense, v.C);
+    const long long yo = gn_offset(p, ut, v.per_frame, v.H, v.W, v.ys_t, v.ys_h, v.ys_w, v.y_dense, v.C);
+    *reinterpret_cast<uint4*>(yb + yo + vec * 8) = transform(__ldg(reinterpret_cast<const uint4*>(xb + xo + vec * 8)));
   }
 }
 
