@@ -40,7 +40,9 @@ struct ConvTcParams {
   const void* residual;
   void* y;
   long long ys_b, ys_t, ys_h, ys_w, ys_c;
-  int yC, yT, vec_ok;
+  int yC, yT, vec_ok, bias_vec;
+  unsigned long long* trace;  // optional [trace_n][8] globaltimer stamps per CTA (diagnostics)
+  int trace_n;
 };
 
 static constexpr int kThreads = 256;
@@ -100,6 +102,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool traced = p.trace != nullptr && static_cast<int>(blockIdx.x) < p.trace_n;
+  unsigned long long* trc = traced ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (traced && threadIdx.x == 0) trc[0] = ptx::globaltimer_ns();
   const TileCoord tc = decode_tile(p);
   // sub-tiles that contain at least one valid output position
   int nacc_eff;
@@ -133,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (traced && threadIdx.x == 0) trc[1] = ptx::globaltimer_ns();
 
   if (warp == 0) {
     // ------------------------------------------------------------- A producer
@@ -200,8 +206,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       // descriptor high word: SBO = 1024 B (>>4 = 64) at [32,46), version 1 at [46,48), SWIZZLE_128B at [61,64)
       constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
       constexpr uint32_t kDescLoFlags = 1u << 16;  // LBO field (canonical 1 for swizzled K-major)
+      bool first = true;
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&fullA[slotA], phaseA);
+        if (traced && first && lane == 0) trc[2] = ptx::globaltimer_ns();
         // K = 16 per MMA; channels beyond Cin are TMA zero-fill in both operands, skip those MMAs entirely
         const int ch_left = p.Cin - cb * 64;
         const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
@@ -209,6 +217,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int khs = 0; khs < p.KHs; ++khs) {
           wait_bar(&fullB[slotB], phaseB);
           ptx::tc_fence_after();
+          if (traced && first && lane == 0) trc[3] = ptx::globaltimer_ns();
+          first = false;
           const uint32_t b_lo0 = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
           const uint32_t a_lo1 = a_lo0 + static_cast<uint32_t>(khs) * tap_stride16;
           if (ptx::elect_one()) {
@@ -243,15 +253,23 @@ __global__ void __launch_bounds__(kThreads, 1)
       });
       if (ptx::elect_one()) ptx::umma_commit(accFull);
       __syncwarp();
+      if (traced && lane == 0) trc[4] = ptx::globaltimer_ns();
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------- epilogue
+  }
+  {
+    // ------------------------------------------------------------- epilogue (all 8 warps)
+    // Warps 4-7 arrive here at once, warps 0-2 when their role loops have issued everything, warp 3 after the
+    // TMEM allocation.  Warp w may touch TMEM lanes 32*(w%4)..+31, so two warps share each lane quarter and
+    // split the (sub-tile, 32-column chunk) work items between them.
     using E = Elem<DT>;
-    const int q = warp - 4;                 // TMEM lane quarter
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int grp = warp >> 2;              // which half of the work items
     const int r = q * 32 + lane;            // accumulator row owned by this thread
     wait_bar(accFull, 0);
     ptx::tc_fence_after();
+    if (traced && threadIdx.x == 128) trc[5] = ptx::globaltimer_ns();
     const int chalf = p.up_time == 2 ? p.Cout / 2 : p.Cout;
+    int item = 0;
     for (int s = 0; s < nacc_eff; ++s) {
       int h, w;
       if (p.flat) {
@@ -267,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int c0 = 0; c0 < p.N_cta; c0 += 32) {
         const int cg0 = tc.n0 + c0;
         if (cg0 >= p.Cout) break;  // warp-uniform
+        if (((item++) & 1) != grp) continue;  // warp-uniform
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s * p.N_cta + c0), v);
         ptx::tmem_ld_wait();
@@ -309,26 +328,35 @@ __global__ void __launch_bounds__(kThreads, 1)
           typename E::T* yp = reinterpret_cast<typename E::T*>(p.y) + off + cbase;
           const typename E::T* rp =
               p.residual ? reinterpret_cast<const typename E::T*>(p.residual) + off + cbase : nullptr;
+          float bv[32];
+          if (p.bias && !(p.flags & CVVAE_CONV_BIAS_ALONG_M)) {
+            if (p.bias_vec) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cg0) + g);
+                bv[4 * g] = b4.x; bv[4 * g + 1] = b4.y; bv[4 * g + 2] = b4.z; bv[4 * g + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) bv[c] = __ldg(p.bias + cg0 + c);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) bv[c] = bias_m;
+          }
+          // residual: issue all four 128-bit loads before the arithmetic
+          uint4 rv4[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rv4[g] = rp ? __ldg(reinterpret_cast<const uint4*>(rp) + g) : make_uint4(0, 0, 0, 0);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint4 rv = make_uint4(0, 0, 0, 0);
-            if (rp) rv = __ldg(reinterpret_cast<const uint4*>(rp) + g);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint32_t rw[4] = {rv4[g].x, rv4[g].y, rv4[g].z, rv4[g].w};
             uint32_t ow[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int c = g * 8 + j * 2;
-              float a0 = __uint_as_float(v[c]) * p.alpha;
-              float a1 = __uint_as_float(v[c + 1]) * p.alpha;
-              if (p.bias) {
-                if (p.flags & CVVAE_CONV_BIAS_ALONG_M) {
-                  a0 += bias_m;
-                  a1 += bias_m;
-                } else {
-                  a0 += __ldg(p.bias + cg0 + c);
-                  a1 += __ldg(p.bias + cg0 + c + 1);
-                }
-              }
+              float a0 = fmaf(__uint_as_float(v[c]), p.alpha, bv[c]);
+              float a1 = fmaf(__uint_as_float(v[c + 1]), p.alpha, bv[c + 1]);
               if (rp) {
                 float2 rf = E::to_f2(rw[j]);
                 a0 += rf.x;
@@ -360,11 +388,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
 
+  if (traced && threadIdx.x == 128) trc[6] = ptx::globaltimer_ns();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 3) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (traced && lane == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trc[7] = (ptx::globaltimer_ns() & 0xFFFFFFFFFFFFull) | (static_cast<unsigned long long>(smid) << 48);
+    }
   }
 }
 
@@ -413,6 +447,13 @@ bool conv_tc_eligible(const cvvae_conv_desc* d, const char** why) {
   return true;
 }
 
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_n = 0;
+void conv_tc_set_trace(unsigned long long* buf, int n) {
+  g_trace_buf = buf;
+  g_trace_n = n;
+}
+
 int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   const char* why = nullptr;
   if (!conv_tc_eligible(d, &why)) {
@@ -441,6 +482,9 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.y = y.ptr;
   p.ys_b = y.s_b; p.ys_t = y.s_t; p.ys_h = y.s_h; p.ys_w = y.s_w; p.ys_c = y.s_c;
   p.yC = y.C; p.yT = y.T;
+  p.trace = g_trace_buf;
+  p.trace_n = g_trace_n;
+  p.bias_vec = d->bias && (reinterpret_cast<uintptr_t>(d->bias) % 16 == 0);
   CVVAE_CHECK_ARG(y.B == x.B, "conv: batch mismatch");
   CVVAE_CHECK_ARG(y.C == (p.up_time == 2 ? d->Cout / 2 : d->Cout), "conv: y.C %d inconsistent with Cout %d / up_time %d",
                   y.C, d->Cout, p.up_time);
@@ -559,6 +603,11 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
 }
 
 }  // namespace cvvae
+
+extern "C" int cvvae_conv_tc_set_trace(void* device_buf, int32_t n_ctas) {
+  cvvae::conv_tc_set_trace(static_cast<unsigned long long*>(device_buf), device_buf ? n_ctas : 0);
+  return CVVAE_OK;
+}
 
 extern "C" int cvvae_conv3d_tc(const cvvae_conv_desc* d, void* stream) {
   CVVAE_CHECK_ARG(d && cvvae::tensor_ok(&d->x) && cvvae::tensor_ok(&d->y) && d->w, "cvvae_conv3d_tc: null argument");

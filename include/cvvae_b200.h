@@ -146,6 +146,10 @@ int cvvae_blend(const cvvae_tensor5* a, const cvvae_tensor5* b, int32_t overlap,
                 void* stream);
 
 /* Diagnostics */
+/* Per-CTA phase timestamps of the next conv_tc launches: device buffer of n_ctas x 8 uint64 (globaltimer ns:
+ * entry, setup done, first A landed, first B landed, all MMAs issued, accumulators ready, epilogue done,
+ * exit | smid<<48).  Pass NULL to switch off. */
+int cvvae_conv_tc_set_trace(void* device_buf, int32_t n_ctas);
 const char* cvvae_last_error(void);
 int cvvae_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process (all threads). */
