@@ -41,6 +41,7 @@ struct ConvTcParams {
   void* y;
   long long ys_b, ys_t, ys_h, ys_w, ys_c;
   int yC, yT, vec_ok, bias_vec;
+  int tma_epi, box_w;  // epilogue through swizzled smem + TMA store (box_w = min(TW, 32) positions per box row)
   unsigned long long* trace;  // optional [trace_n][8] globaltimer stamps per CTA (diagnostics)
   int trace_n;
 };
@@ -87,6 +88,7 @@ __device__ __forceinline__ void for_each_slab(const ConvTcParams& p, int t, F&& 
 template <int DT>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                    const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* emptyB = bars + 24;   // [8]
   uint64_t* accFull = bars + 32;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
+  uint64_t* resBar = bars + 40;   // [8] one per warp: residual tile landed (TMA epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::mbar_init(&emptyB[i], 1);
     }
     ptx::mbar_init(accFull, 1);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&resBar[i], 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -270,6 +274,127 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (traced && threadIdx.x == 128) trc[5] = ptx::globaltimer_ns();
     const int chalf = p.up_time == 2 ? p.Cout / 2 : p.Cout;
     int item = 0;
+    if (p.tma_epi) {
+      // ---- TMEM -> registers -> SWIZZLE_128B staging tile (32 positions x 64 channels, 4 KB) -> TMA store.
+      // A warp's direct 16-byte stores would touch 32 different 128-byte lines per instruction (position stride
+      // = C*2 bytes); the bulk tensor store writes full lines and clips partial tiles by itself.  The residual
+      // tile comes in the same way (TMA load into the staging tile, added in place).  Staging reuses the drained
+      // A ring: two 4 KB tiles per warp.
+      uint8_t* stage = sA + static_cast<size_t>(warp) * 8192;
+      uint32_t res_phase = 0;
+      int nbuf = 0;
+      const int r0 = q * 32;
+      const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+      const uint32_t sw = static_cast<uint32_t>(lane & 7);
+      for (int s = 0; s < nacc_eff; ++s) {
+        int h, w, h_me, w_me;
+        if (p.flat) {
+          h = 0;
+          w = tc.w0 + s * 128 + r0;
+          h_me = 0;
+          w_me = w + lane;
+        } else {
+          h = tc.h0 + s * p.ROWS + r0 / p.TW;
+          w = tc.w0 + r0 % p.TW;
+          h_me = tc.h0 + s * p.ROWS + (r0 + lane) / p.TW;
+          w_me = tc.w0 + (r0 + lane) % p.TW;
+        }
+        float bias_m = 0.f;
+        if (p.bias && (p.flags & CVVAE_CONV_BIAS_ALONG_M)) {
+          const long long m_index =
+              ((static_cast<long long>(tc.b) * p.T_out + tc.t) * p.H_out + h_me) * static_cast<long long>(p.W_out) + w_me;
+          if (h_me < p.H_out && w_me < p.W_out) bias_m = __ldg(p.bias + m_index);
+        }
+        for (int c0 = 0; c0 < p.N_cta; c0 += 64) {
+          const int cg0 = tc.n0 + c0;
+          if (cg0 >= p.Cout) break;               // warp-uniform
+          if (((item++) & 1) != grp) continue;    // warp-uniform
+          int cbase = cg0, t_o = tc.t;
+          if (p.up_time == 2) {
+            const int n_il = cg0 / chalf;
+            cbase = cg0 - n_il * chalf;
+            t_o = 2 * tc.t + n_il - 1;
+            if (t_o < 0) continue;
+          }
+          uint8_t* tile = stage + (nbuf & 1) * 4096;
+          const uint32_t tile_u32 = ptx::smem_u32(tile);
+          // the bulk store that last read this buffer (two items ago) must be done reading
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          if (p.residual) {
+            if (lane == 0) {
+              ptx::mbar_expect_tx(&resBar[warp], 4096);
+              ptx::tma_load_5d(tile, &tmR, &resBar[warp], cbase, w, h, t_o, tc.b);
+            }
+            wait_bar(&resBar[warp], res_phase);
+            res_phase ^= 1;
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cc0 = c0 + half * 32;
+            uint32_t v[32];
+            if (cc0 < p.N_cta) {
+              ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s * p.N_cta + cc0), v);
+              ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = 0u;
+            }
+            float bv[32];
+            const int cgh = tc.n0 + cc0;
+            if (p.bias && !(p.flags & CVVAE_CONV_BIAS_ALONG_M) && cgh + 32 <= p.Cout) {
+              if (p.bias_vec) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cgh) + g);
+                  bv[4 * g] = b4.x; bv[4 * g + 1] = b4.y; bv[4 * g + 2] = b4.z; bv[4 * g + 3] = b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) bv[c] = __ldg(p.bias + cgh + c);
+              }
+            } else if (p.bias && !(p.flags & CVVAE_CONV_BIAS_ALONG_M)) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) bv[c] = (cgh + c < p.Cout) ? __ldg(p.bias + cgh + c) : 0.f;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) bv[c] = bias_m;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+              const uint32_t addr = tile_u32 + row_off + ((chunk ^ sw) << 4);
+              uint4 rv = make_uint4(0, 0, 0, 0);
+              if (p.residual) rv = ptx::ld_shared_v4(addr);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = j * 8 + e * 2;
+                float a0 = fmaf(__uint_as_float(v[c]), p.alpha, bv[c]);
+                float a1 = fmaf(__uint_as_float(v[c + 1]), p.alpha, bv[c + 1]);
+                if (p.residual) {
+                  const float2 rf = E::to_f2(rw[e]);
+                  a0 += rf.x;
+                  a1 += rf.y;
+                }
+                ow[e] = E::pack2(a0, a1);
+              }
+              ptx::st_shared_v4(addr, ow[0], ow[1], ow[2], ow[3]);
+            }
+          }
+          ptx::fence_proxy_async();   // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_5d(&tmY, tile, cbase, w, h, t_o, tc.b);
+            ptx::bulk_commit();
+          }
+          ++nbuf;
+        }
+      }
+      if (lane == 0) ptx::bulk_wait<0>();
+      __syncwarp();
+    } else
     for (int s = 0; s < nacc_eff; ++s) {
       int h, w;
       if (p.flat) {
@@ -588,6 +713,26 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     if (!encode_map(&tmB, d->w, 3, dims, strides, box, estr)) return CVVAE_E_CUDA;
   }
 
+  // ---- epilogue through shared memory + TMA store where the output is a plain channels-last 16-bit tensor
+  CUtensorMap tmY = tmA, tmR = tmA;
+  p.tma_epi = 0;
+  {
+    const int chalf = p.up_time == 2 ? p.Cout / 2 : p.Cout;
+    const bool ok = p.vec_ok && !(d->flags & CVVAE_CONV_OUT_F32) && (p.up_time == 1 || chalf % 64 == 0) &&
+                    (static_cast<size_t>(NA) * p.slab_bytes >= 65536);
+    if (ok) {
+      p.box_w = p.flat ? 32 : (p.TW < 32 ? p.TW : 32);
+      cuuint64_t dims[5] = {(cuuint64_t)y.C, (cuuint64_t)y.W, (cuuint64_t)y.H, (cuuint64_t)y.T, (cuuint64_t)y.B};
+      cuuint64_t strides[4] = {(cuuint64_t)y.s_w * 2, (cuuint64_t)y.s_h * 2, (cuuint64_t)y.s_t * 2, (cuuint64_t)y.s_b * 2};
+      for (int i = 0; i < 4; ++i)
+        if (dims[i + 1] == 1 && (strides[i] == 0 || strides[i] % 16)) strides[i] = (cuuint64_t)y.C * 2;
+      cuuint32_t box[5] = {64, (cuuint32_t)p.box_w, (cuuint32_t)(32 / p.box_w), 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+      if (!encode_map(&tmY, y.ptr, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
+      if (d->residual && !encode_map(&tmR, d->residual, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
+      p.tma_epi = 1;
+    }
+  }
+
   const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_h * p.B;
   CVVAE_CHECK_ARG(grid > 0 && grid < (1ll << 31), "conv_tc: grid size %lld out of range", grid);
   CVVAE_DISPATCH_DTYPE(d->dtype, {
@@ -596,7 +741,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
       CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
       attr_set = true;
     }
-    conv_tc_kernel<DT><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(tmA, tmB, p);
+    conv_tc_kernel<DT><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(tmA, tmB, tmY, tmR, p);
   });
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;

@@ -1,0 +1,51 @@
+"""Size-independent properties at BASELINE.json's full size (17x3x576x1024, fp16, default tiling) where the oracle is
+too slow to run: determinism, wrapper == manual tile assembly (blend order, crops, chunking), finiteness."""
+import pytest
+import torch
+
+from oracle import cvvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _model():
+    from cvvae_b200 import CVVAEModel
+    torch.manual_seed(7)
+    m = CVVAEModel()
+    g = torch.Generator().manual_seed(8)
+    for k, p in m.named_parameters():
+        if p.dim() == 1:
+            p.data.copy_(torch.rand(p.shape, generator=g) * (0.4 if k.endswith("bias") else 1.0) + (-0.2 if k.endswith("bias") else 0.5))
+    return m.half().cuda()
+
+
+def test_c2_shape_properties():
+    m = _model()
+    x = O.synthetic_video((1, 3, 17, 576, 1024), 5).half().cuda()
+    mom1 = m.encode(x).latent_dist.parameters
+    mom2 = m.encode(x).latent_dist.parameters
+    assert mom1.shape == (1, 8, 5, 72, 128)
+    assert torch.equal(mom1, mom2), "encode is not deterministic"
+    assert torch.isfinite(mom1).all()
+    # wrapper == manual assembly: 2 tiles at w = 0 and 448, blend_h over 16 latent columns (modeling_vae.py:148-190)
+    t0 = m.encoder(x[:, :, :, :, 0:576])
+    t1 = m.encoder(x[:, :, :, :, 448:1024])
+    t1 = O.blend_h(t0, t1.clone(), 16)
+    manual = torch.cat([t0[:, :, :, :, :56], t1], dim=4)
+    assert torch.equal(manual, mom1), "tiled encode differs from manual tile assembly"
+    z = mom1[:, :4].contiguous()
+    rec1 = m.decode(z).sample
+    rec2 = m.decode(z).sample
+    assert rec1.shape == x.shape and torch.equal(rec1, rec2) and torch.isfinite(rec1).all()
+    d0 = m.decoder(z[:, :, :, :, 0:72])
+    d1 = m.decoder(z[:, :, :, :, 56:128])
+    d1 = O.blend_h(d0, d1.clone(), 128)
+    assert torch.equal(torch.cat([d0[:, :, :, :, :448], d1], dim=4), rec1), "tiled decode differs from manual assembly"
+
+
+def test_batch_items_are_independent():
+    m = _model()
+    x = O.synthetic_video((2, 3, 5, 64, 96), 6).half().cuda()
+    both = m.encode(x).latent_dist.parameters
+    one = m.encode(x[1:2].contiguous()).latent_dist.parameters
+    assert torch.equal(both[1:2], one)
