@@ -305,6 +305,10 @@ def main():
                 "peak_source": peak_src, "algorithmic_tflop_per_step": tc["flops"] / args.steps / 1e12,
                 "kernel_ms_per_step": tc["ms"] / args.steps, "launches_per_step": tc["launches"] / args.steps,
                 "share_of_step": tc["ms"] / ms_total,
+                # the up-sampling convs run as folded 2x2 phase kernels (2.25x fewer MACs than the reference issues);
+                # `achieved` counts EXECUTED FLOPs, this is the same time against the reference's dense count
+                "reference_dense_tflop_per_step": tc["ref_flops"] / args.steps / 1e12,
+                "achieved_vs_reference_count": tc["ref_flops"] / (tc["ms"] * 1e-3) / 1e12,
                 "conv_direct_ms_per_step": prof["conv_direct"]["ms"] / args.steps}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

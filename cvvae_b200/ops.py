@@ -52,8 +52,8 @@ class CudaOps:
         self.profile = None  # None | {"flops": {path: int}, "events": {path: [(start, end), ...]}}
 
     def start_profile(self):
-        self.profile = {"flops": {"conv_tc": 0, "conv_direct": 0}, "events": {"conv_tc": [], "conv_direct": []},
-                        "launches": {"conv_tc": 0, "conv_direct": 0}}
+        self.profile = {"flops": {"conv_tc": 0, "conv_direct": 0}, "ref_flops": {"conv_tc": 0, "conv_direct": 0},
+                        "events": {"conv_tc": [], "conv_direct": []}, "launches": {"conv_tc": 0, "conv_direct": 0}}
 
     def stop_profile(self):
         """Returns {path: {"flops": F, "ms": T, "launches": n}} (synchronises)."""
@@ -62,7 +62,8 @@ class CudaOps:
         out = {}
         for path in prof["flops"]:
             ms = sum(s.elapsed_time(e) for s, e in prof["events"][path])
-            out[path] = {"flops": prof["flops"][path], "ms": ms, "launches": prof["launches"][path]}
+            out[path] = {"flops": prof["flops"][path], "ref_flops": prof["ref_flops"][path], "ms": ms,
+                         "launches": prof["launches"][path]}
         return out
 
     # ------------------------------------------------------------------ memory (plumbing)
@@ -92,7 +93,7 @@ class CudaOps:
              stride=(1, 1, 1), offset=(0, 0, 0), pad_t=L.PAD_ZERO, pad_hw=L.PAD_ZERO, up_time=1,
              residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
              out_f32: bool = False, bias_along_m: bool = False, w_ld: int = 0, cout: Optional[int] = None,
-             force: Optional[str] = None) -> torch.Tensor:
+             force: Optional[str] = None, ref_taps: Optional[int] = None) -> torch.Tensor:
         """y = alpha * conv(x, w) + bias + residual.  ``w`` is packed [taps, Cout, Cin(ld)]."""
         B, T, H, W, Ci = x.shape
         kt, kh, kw = kernel
@@ -128,8 +129,11 @@ class CudaOps:
             return out
         path = "conv_tc" if (force == "tc" or (force is None and self.lib.cvvae_conv3d_is_tc(C.byref(d)))) else "conv_direct"
         t_conv = (out.shape[1] + 1) // 2 if up_time == 2 else out.shape[1]
-        # dense algorithmic count of what the reference issues: 2 * M * N * K (zero-padded taps included)
-        self.profile["flops"][path] += 2 * B * t_conv * out.shape[2] * out.shape[3] * Co * kt * kh * kw * Ci
+        # executed: 2 * M * N * K of this launch (zero-padded taps included).  reference-dense: the same output
+        # positions at the tap count the reference issues (27 for the folded up-sample phases, ref_taps)
+        mn = 2 * B * t_conv * out.shape[2] * out.shape[3] * Co * Ci
+        self.profile["flops"][path] += mn * kt * kh * kw
+        self.profile["ref_flops"][path] += mn * (ref_taps if ref_taps is not None else kt * kh * kw)
         self.profile["launches"][path] += 1
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_ev.record()

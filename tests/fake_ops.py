@@ -45,7 +45,7 @@ class FakeOps:
 
     def conv(self, x, w, bias, *, kernel=(1, 1, 1), stride=(1, 1, 1), offset=(0, 0, 0), pad_t=PAD_ZERO, pad_hw=PAD_ZERO,
              up_time=1, residual=None, alpha=1.0, out=None, out_f32=False, bias_along_m=False, w_ld=0, cout=None,
-             force=None):
+             force=None, ref_taps=None):
         self.launches += 1
         assert out is not None
         kt, kh, kw = kernel

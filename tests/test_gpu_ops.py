@@ -91,6 +91,10 @@ CONV_CASES = {
     "res_bias_alpha": ((1, 2, 16, 24, 64), 128, (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1,
                        {"residual": True, "alpha": 0.5}),
     "wide512": ((1, 2, 24, 24, 512), 512, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "phase322_up": ((1, 3, 16, 24, 64), 128, (3, 2, 2), (1, 1, 1), ((1, 1), (1, 0), (0, 1)), PAD_REPLICATE, PAD_ZERO, 2,
+                    {"lattice_out": (0, 1)}),
+    "phase322": ((1, 2, 20, 16, 128), 256, (3, 2, 2), (1, 1, 1), ((1, 1), (0, 1), (1, 0)), PAD_REPLICATE, PAD_ZERO, 1,
+                 {"lattice_out": (1, 0)}),
     "conv1x1_spatial": ((1, 2, 20, 20, 128), 256, (1, 1, 1), (1, 1, 1), ((0, 0), (0, 0), (0, 0)), PAD_ZERO, PAD_ZERO, 1,
                         {"strided_in": True}),
 }
@@ -114,6 +118,10 @@ def _run_conv(ops, fake, case, dtype, force):
     yshape = (B, 2 * To - 1, Ho, Wo, Co // 2) if up_time == 2 else (B, To, Ho, Wo, Co)
 
     def mk_out():
+        if ex.get("lattice_out"):  # one (ph::2, pw::2) lattice of a 2x larger tensor (folded up-sample phases)
+            ph, pw = ex["lattice_out"]
+            big = torch.zeros((yshape[0], yshape[1], 2 * yshape[2], 2 * yshape[3], yshape[4]), dtype=dtype, device=DEV)
+            return big[:, :, ph::2, pw::2, :]
         if ex.get("ncdhw_out"):
             return torch.zeros((yshape[0], yshape[4], yshape[1], yshape[2], yshape[3]), dtype=dtype, device=DEV).permute(0, 2, 3, 4, 1)
         return torch.zeros(yshape, dtype=dtype, device=DEV)
