@@ -34,6 +34,7 @@ class ConvDesc(C.Structure):
         ("pad_t", C.c_int32), ("pad_hw", C.c_int32),
         ("up_time", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_int32),
         ("alpha", C.c_float),
+        ("gn_stats", C.c_void_p), ("gn_groups", C.c_int32),
     ]
 
 

@@ -118,6 +118,10 @@ int conv_direct_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   CVVAE_CHECK_ARG(y.B == x.B, "conv: batch mismatch");
   CVVAE_CHECK_ARG(y.C == (p.up_time == 2 ? d->Cout / 2 : d->Cout), "conv: y.C %d inconsistent with Cout %d / up_time %d",
                   y.C, d->Cout, p.up_time);
+  if (d->gn_stats) {
+    set_error("conv_direct: fused GroupNorm statistics are a tensor-core epilogue feature");
+    return CVVAE_E_UNSUPPORTED;
+  }
   p.P = 1ll * p.B * p.T_out * p.H_out * p.W_out;
   const long long gx = (p.P + 127) / 128;
   CVVAE_CHECK_ARG(gx > 0 && gx < (1ll << 31), "conv_direct: grid out of range");
@@ -144,6 +148,8 @@ __global__ void pack_weight_kernel(const typename Elem<DT>::T* __restrict__ src,
 
 bool conv_tc_eligible(const cvvae_conv_desc* d, const char** why);
 int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream);
+int gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats, int32_t dtype,
+                 cudaStream_t stream, bool zero_first);
 
 }  // namespace cvvae
 
@@ -152,11 +158,22 @@ extern "C" int cvvae_conv3d_direct(const cvvae_conv_desc* d, void* stream) {
   return cvvae::conv_direct_launch(d, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int cvvae_conv3d(const cvvae_conv_desc* d, void* stream) {
+extern "C" int cvvae_conv3d(const cvvae_conv_desc* d, void* stream_) {
   CVVAE_CHECK_ARG(d && cvvae::tensor_ok(&d->x) && cvvae::tensor_ok(&d->y) && d->w, "cvvae_conv3d: null argument");
-  if (!(d->flags & CVVAE_CONV_FORCE_DIRECT) && cvvae::conv_tc_eligible(d, nullptr))
-    return cvvae::conv_tc_launch(d, static_cast<cudaStream_t>(stream));
-  return cvvae::conv_direct_launch(d, static_cast<cudaStream_t>(stream));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool tc = !(d->flags & CVVAE_CONV_FORCE_DIRECT) && cvvae::conv_tc_eligible(d, nullptr);
+  if (!d->gn_stats) return tc ? cvvae::conv_tc_launch(d, stream) : cvvae::conv_direct_launch(d, stream);
+  // consumer GroupNorm sums requested: fused in the tensor-core epilogue when that path can, otherwise one extra
+  // statistics pass over y - either way `gn_stats` has y's sums added when the call returns
+  if (tc) {
+    const int rc = cvvae::conv_tc_launch(d, stream);
+    if (rc != CVVAE_E_UNSUPPORTED) return rc;
+  }
+  cvvae_conv_desc plain = *d;
+  plain.gn_stats = nullptr;
+  int rc = tc ? cvvae::conv_tc_launch(&plain, stream) : cvvae::conv_direct_launch(&plain, stream);
+  if (rc) return rc;
+  return cvvae::gn_stats_run(&d->y, d->gn_groups, 0, d->gn_stats, d->dtype, stream, false);
 }
 
 extern "C" int cvvae_conv3d_is_tc(const cvvae_conv_desc* d) {

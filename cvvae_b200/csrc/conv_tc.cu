@@ -41,6 +41,8 @@ struct ConvTcParams {
   void* y;
   long long ys_b, ys_t, ys_h, ys_w, ys_c;
   int yC, yT, vec_ok, bias_vec;
+  double* gn_stats;  // fused GroupNorm statistics of y (TMA epilogue only)
+  int gn_groups, gn_cpg;
   int tma_epi, box_w;  // epilogue through swizzled smem + TMA store (box_w = min(TW, 32) positions per box row)
   unsigned long long* trace;  // optional [trace_n][8] globaltimer stamps per CTA (diagnostics)
   int trace_n;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* accFull = bars + 32;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
   uint64_t* resBar = bars + 40;   // [8] one per warp: residual tile landed (TMA epilogue)
+  float* gn_bins = reinterpret_cast<float*>(bars + 64);  // [64 groups][2] per-CTA partial GroupNorm sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     nacc_eff = min(p.NACC, (rem + p.ROWS - 1) / p.ROWS);
   }
 
+  if (threadIdx.x < 128) gn_bins[threadIdx.x] = 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NA; ++i) {
       ptx::mbar_init(&fullA[i], 1);
@@ -383,6 +387,42 @@ __global__ void __launch_bounds__(kThreads, 1)
               ptx::st_shared_v4(addr, ow[0], ow[1], ow[2], ow[3]);
             }
           }
+          if (p.gn_stats) {
+            // GroupNorm statistics of the consumer, from the staged (already rounded) tile: lane l owns channels
+            // 2l, 2l+1 of this 64-channel group and walks the 32 rows (conflict-free: one 128-byte row per step)
+            __syncwarp();
+            const unsigned valid = __ballot_sync(0xffffffffu, (h_me < p.H_out) && (w_me < p.W_out));
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const uint32_t chunk = static_cast<uint32_t>(lane >> 2), word = static_cast<uint32_t>(lane & 3) * 4u;
+            for (int rr = 0; rr < 32; ++rr) {
+              if (!((valid >> rr) & 1u)) continue;
+              uint32_t u;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(tile_u32 + rr * 128u + ((chunk ^ (rr & 7u)) << 4) + word));
+              const float2 f = E::to_f2(u);
+              s0 += f.x; q0 = fmaf(f.x, f.x, q0);
+              s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+            }
+            const int ch = cbase + 2 * lane;
+            if (p.gn_cpg >= 2) {
+              float ts = s0 + s1, tq = q0 + q1;
+              for (int o = 1; o < (p.gn_cpg >> 1) && o < 32; o <<= 1) {
+                ts += __shfl_xor_sync(0xffffffffu, ts, o);
+                tq += __shfl_xor_sync(0xffffffffu, tq, o);
+              }
+              const int lanes_per_group = min(p.gn_cpg >> 1, 32);
+              if ((lane % lanes_per_group) == 0 && ch < p.yC) {
+                atomicAdd(&gn_bins[(ch / p.gn_cpg) * 2], ts);
+                atomicAdd(&gn_bins[(ch / p.gn_cpg) * 2 + 1], tq);
+              }
+            } else if (ch < p.yC) {  // one channel per group
+              atomicAdd(&gn_bins[ch * 2], s0);
+              atomicAdd(&gn_bins[ch * 2 + 1], q0);
+              if (ch + 1 < p.yC) {
+                atomicAdd(&gn_bins[(ch + 1) * 2], s1);
+                atomicAdd(&gn_bins[(ch + 1) * 2 + 1], q1);
+              }
+            }
+          }
           ptx::fence_proxy_async();   // generic-proxy writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
@@ -516,6 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (traced && threadIdx.x == 128) trc[6] = ptx::globaltimer_ns();
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.gn_stats && static_cast<int>(threadIdx.x) < 2 * p.gn_groups) {
+    const float vsum = gn_bins[threadIdx.x];
+    if (vsum != 0.f) atomicAdd(p.gn_stats + static_cast<size_t>(tc.b) * 2 * p.gn_groups + threadIdx.x, static_cast<double>(vsum));
+  }
   if (warp == 3) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
@@ -672,7 +716,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128, N_cta);
 
   // ---- shared memory budget: 227 KB - alignment slack - barriers
-  const size_t budget = 232448 - 1024 - 512;
+  const size_t budget = 232448 - 1024 - 1024;
   int NB = 4;
   while (NB > 2 && static_cast<size_t>(NB) * p.b_bytes + 2ull * p.slab_bytes > budget) --NB;
   size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;
@@ -683,7 +727,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_bytes <= budget) ++NB;
   p.NA = NA;
   p.NB = NB;
-  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 512;
+  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 1024;
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
@@ -731,6 +775,21 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
       if (d->residual && !encode_map(&tmR, d->residual, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
       p.tma_epi = 1;
     }
+  }
+  // fused GroupNorm statistics need the TMA epilogue, power-of-two channels per group and one sample per CTA index
+  p.gn_stats = nullptr;
+  if (d->gn_stats) {
+    const int cpg = d->gn_groups > 0 ? y.C / d->gn_groups : 0;
+    const bool ok = p.tma_epi && d->gn_groups > 0 && d->gn_groups <= 64 && y.C % d->gn_groups == 0 && cpg >= 1 &&
+                    (cpg & (cpg - 1)) == 0 && (cpg <= 64 ? 64 % cpg == 0 : cpg % 64 == 0);
+    if (!ok) {
+      set_error("conv_tc: fused GroupNorm statistics unsupported for this output (C=%d groups=%d tma_epi=%d)", y.C,
+                d->gn_groups, p.tma_epi);
+      return CVVAE_E_UNSUPPORTED;
+    }
+    p.gn_stats = d->gn_stats;
+    p.gn_groups = d->gn_groups;
+    p.gn_cpg = cpg;
   }
 
   const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_h * p.B;

@@ -323,15 +323,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const GnView v, long lon
 
 using namespace cvvae;
 
+namespace cvvae {
+int gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats, int32_t dtype,
+                 cudaStream_t stream, bool zero_first);
+}
+
 extern "C" int cvvae_groupnorm_stats(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats,
                                      int32_t dtype, void* stream_) {
   CVVAE_CHECK_ARG(tensor_ok(x) && stats, "cvvae_groupnorm_stats: null argument");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return cvvae::gn_stats_run(x, groups, per_frame, stats, dtype, static_cast<cudaStream_t>(stream_), true);
+}
+
+int cvvae::gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats, int32_t dtype,
+                        cudaStream_t stream, bool zero_first) {
   GnView v{};
   int rc = fill_view(v, x, nullptr, groups, per_frame);
   if (rc) return rc;
   const int units = per_frame ? x->B * x->T : x->B;
-  CVVAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * units, stream));
+  if (zero_first) CVVAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * units, stream));
   dim3 grid;
   pick_grid(v, units, grid);
   CVVAE_DISPATCH_DTYPE(dtype, { gn_stats_kernel<DT><<<grid, 256, 0, stream>>>(v, stats); });

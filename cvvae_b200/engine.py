@@ -53,12 +53,14 @@ class NetConfig:
 
 
 class Act:
-    """An activation: logical [B,T,H,W,C] tensor, plus (sd3) the framed buffer it is the interior of."""
-    __slots__ = ("t", "pad")
+    """An activation: logical [B,T,H,W,C] tensor, plus (sd3) the framed buffer it is the interior of, plus - when
+    the producing convolution computed them in its epilogue - the GroupNorm sums of its consumer."""
+    __slots__ = ("t", "pad", "stats")
 
-    def __init__(self, t: torch.Tensor, pad: Optional[torch.Tensor] = None):
+    def __init__(self, t: torch.Tensor, pad: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None):
         self.t = t
         self.pad = pad
+        self.stats = stats
 
 
 def prepack_params(state_dict: Dict[str, torch.Tensor], ops, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -124,8 +126,12 @@ class Engine:
 
     def conv(self, a: Act, name: str, *, kernel, stride=(1, 1, 1), pads, pad_t, pad_hw, up_time=1,
              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-             weight_key: Optional[str] = None, ref_taps: Optional[int] = None) -> Act:
-        """Convolution with the reference's padding expressed as ((t_lo,t_hi),(h_lo,h_hi),(w_lo,w_hi))."""
+             weight_key: Optional[str] = None, ref_taps: Optional[int] = None,
+             stats: Optional[torch.Tensor] = None, want_stats: bool = False) -> Act:
+        """Convolution with the reference's padding expressed as ((t_lo,t_hi),(h_lo,h_hi),(w_lo,w_hi)).
+
+        want_stats: also produce the consumer GroupNorm's (sum, sum^2) per (sample, group) in the epilogue
+        (`stats` continues an accumulator across the launches that fill one tensor)."""
         x = a.t
         w = self.p[weight_key or (name + ".weight")]
         b = self.p.get(name + ".bias")
@@ -165,16 +171,26 @@ class Engine:
             pad_hw = PAD_ZERO
         flat = (kernel == (1, 1, 1) and stride == (1, 1, 1) and x.is_contiguous() and out.is_contiguous()
                 and (residual is None or residual.is_contiguous()) and up_time == 1)
+        yC = yshape[4]
+        cpg = yC // self.cfg.groups if yC % self.cfg.groups == 0 else 0
+        stats_ok = (cpg >= 1 and (cpg & (cpg - 1)) == 0 and out.stride(4) == 1 and yC % 8 == 0
+                    and all(st_ % 8 == 0 for st_ in out.stride()[:4]) and (not flat or B == 1))
+        if (want_stats or stats is not None) and stats_ok:
+            if stats is None:
+                stats = self.ops.new_stats(B, self.cfg.groups, x.device)
+        else:
+            stats = None
+        skw = dict(gn_stats=stats, gn_groups=self.cfg.groups) if stats is not None else {}
         if flat:
             P = B * T * H * W
             xf = x.view(1, 1, 1, P, x.shape[4])
             of = out.view(1, 1, 1, P, Co)
             rf = residual.view(1, 1, 1, P, Co) if residual is not None else None
-            self.ops.conv(xf, w, b, kernel=kernel, residual=rf, out=of)
+            self.ops.conv(xf, w, b, kernel=kernel, residual=rf, out=of, **skw)
         else:
             self.ops.conv(x, w, b, kernel=kernel, stride=stride, offset=off, pad_t=pad_t, pad_hw=pad_hw,
-                          up_time=up_time, residual=residual, out=out, ref_taps=ref_taps)
-        return Act(out)
+                          up_time=up_time, residual=residual, out=out, ref_taps=ref_taps, **skw)
+        return Act(out, stats=stats)
 
     def conv3(self, a: Act, name: str, causal: bool, **kw) -> Act:
         """3x3x3, stride 1, 'same': CausalConv3d / nn.Conv3d(padding=1) / Conv3d(replicate)."""
@@ -195,20 +211,21 @@ class Engine:
     def gn(self, a: Act, name: str, *, silu=True, per_frame=False, framed=False) -> Act:
         x = a.t
         g, b = self.p[name + ".weight"], self.p[name + ".bias"]
+        skw = dict(stats=a.stats) if (a.stats is not None and not per_frame) else {}
         if framed:
             B, T, H, W, Cc = x.shape
             pad, inner = self.ops.empty_padded(B, T, H, W, Cc, x.dtype, x.device)
-            self.ops.groupnorm(x, g, b, self.cfg.groups, self.cfg.eps, per_frame=per_frame, silu=silu, out=inner)
+            self.ops.groupnorm(x, g, b, self.cfg.groups, self.cfg.eps, per_frame=per_frame, silu=silu, out=inner, **skw)
             self.ops.replicate_border(pad)
             return Act(inner, pad)
-        return Act(self.ops.groupnorm(x, g, b, self.cfg.groups, self.cfg.eps, per_frame=per_frame, silu=silu))
+        return Act(self.ops.groupnorm(x, g, b, self.cfg.groups, self.cfg.eps, per_frame=per_frame, silu=silu, **skw))
 
     # ------------------------------------------------------------------ blocks
     def resblock(self, a: Act, p: str, causal: bool) -> Act:
         """ResnetBlock3D.forward: vae_models.py:390-410 / vae_blocks3d_sd3.py:518-569."""
         cfg = self.cfg
         h = self.gn(a, p + ".norm1", framed=self.sd3)
-        h = self.conv3(h, p + ".conv1", causal)
+        h = self.conv3(h, p + ".conv1", causal, want_stats=True)
         # conv2 is a zero-padded per-frame 3x3 when half_3d, else another conv_cls 3x3x3
         h = self.gn(h, p + ".norm2", framed=(self.sd3 and not cfg.half_3d))
         sc_name = p + (".conv_shortcut" if self.sd3 else ".nin_shortcut")
@@ -219,9 +236,10 @@ class Engine:
             if not shortcut.is_contiguous():
                 # residual operands share the (dense) output geometry
                 shortcut = self.ops.copy(shortcut, self.ops.empty(shortcut.shape, shortcut.dtype, shortcut.device))
+        # every block output feeds a GroupNorm (next block's norm1 / norm_out) or a conv that ignores the sums
         if cfg.half_3d:
-            return self.conv2(h, p + ".conv2", residual=shortcut)
-        return self.conv3(h, p + ".conv2", causal, residual=shortcut)
+            return self.conv2(h, p + ".conv2", residual=shortcut, want_stats=True)
+        return self.conv3(h, p + ".conv2", causal, residual=shortcut, want_stats=True)
 
     def spatial_attention(self, hn: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v_name: str) -> torch.Tensor:
         """softmax(q k^T / sqrt(C)) v per frame, one head (vae_models.py:446-461,500-528; diffusers Attention).
@@ -266,14 +284,14 @@ class Engine:
         k = self.conv1(hn, p + ".k").t
         o = Act(self.spatial_attention(hn.t, q, k, p + ".v"))
         if attn_type != "spatial-temporal-xformer":
-            return self.conv1(o, p + ".proj_out", residual=x)
+            return self.conv1(o, p + ".proj_out", residual=x, want_stats=True)
         h1 = self.conv1(o, p + ".proj_out")
         hn2 = Act(self.ops.layernorm(h1.t, self.p[p + ".norm_t.weight"], self.p[p + ".norm_t.bias"], 1e-5))
         qt = self.conv1(hn2, p + ".q_t").t
         kt = self.conv1(hn2, p + ".k_t").t
         vt = self.conv1(hn2, p + ".v_t").t
         ot = Act(self.ops.attn_temporal(qt, kt, vt))
-        return self.conv1(ot, p + ".proj_out_t", residual=x)
+        return self.conv1(ot, p + ".proj_out_t", residual=x, want_stats=True)
 
     def attn_sd3(self, a: Act, p: str) -> Act:
         """AttentionWithExtraDim over diffusers Attention (vae_blocks3d_sd3.py:119-147,805-823)."""
@@ -284,7 +302,7 @@ class Engine:
         q = self.conv1(hn, p + ".to_q").t
         k = self.conv1(hn, p + ".to_k").t
         o = Act(self.spatial_attention(hn.t, q, k, p + ".to_v"))
-        return self.conv1(o, p + ".to_out.0", residual=x)
+        return self.conv1(o, p + ".to_out.0", residual=x, want_stats=True)
 
     # ------------------------------------------------------------------ networks
     def encode(self, x: torch.Tensor) -> torch.Tensor:
@@ -294,7 +312,7 @@ class Engine:
         L = len(cfg.widths)
         a = Act(x.permute(0, 2, 3, 4, 1))
         E = "encoder."
-        h = self.conv3(a, E + "conv_in", causal)
+        h = self.conv3(a, E + "conv_in", causal, want_stats=True)
         for lvl in range(L):
             for b in range(cfg.num_res_blocks):
                 name = f"{E}down_blocks.{lvl}.resnets.{b}" if self.sd3 else f"{E}down.{lvl}.block.{b}"
@@ -305,11 +323,11 @@ class Engine:
                     # Downsample3D -> conv_cls(k3, stride, padding=1): vae_blocks3d_sd3.py:200-210
                     tp = (2, 0) if causal else (1, 1)
                     h = self.conv(h, f"{E}down_blocks.{lvl}.downsamplers.0.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
-                                  pads=(tp, (1, 1), (1, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_REPLICATE)
+                                  pads=(tp, (1, 1), (1, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_REPLICATE, want_stats=True)
                 else:
                     # Downsample3D.forward vae_models.py:251-263: zero pad right/bottom, replicate 2 frames in front
                     h = self.conv(h, f"{E}down.{lvl}.downsample.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
-                                  pads=((2, 0), (0, 1), (0, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_ZERO)
+                                  pads=((2, 0), (0, 1), (0, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_ZERO, want_stats=True)
         if self.sd3:
             h = self.resblock(h, E + "mid_block.resnets.0", causal)
             if cfg.mid_block_add_attention:
@@ -333,7 +351,7 @@ class Engine:
         L = len(cfg.widths)
         D = "decoder."
         a = Act(z.permute(0, 2, 3, 4, 1))
-        h = self.conv3(a, D + "conv_in", causal)
+        h = self.conv3(a, D + "conv_in", causal, want_stats=True)
         if self.sd3:
             h = self.resblock(h, D + "mid_block.resnets.0", causal)
             if cfg.mid_block_add_attention:
@@ -381,9 +399,12 @@ class Engine:
         To = _out_len(T, 3, 1, tp[0], tp[1])
         yshape = (B, 2 * To - 1, 2 * H, 2 * W, Co // 2) if up_time == 2 else (B, To, 2 * H, 2 * W, Co)
         y = self.ops.empty(yshape, x.dtype, x.device)
+        stats = None
         for ph in (0, 1):
             for pw in (0, 1):
-                self.conv(a, name, kernel=(3, 2, 2), pads=(tp, (1, 0) if ph == 0 else (0, 1), (1, 0) if pw == 0 else (0, 1)),
-                          pad_t=pad_t, pad_hw=pad_hw, up_time=up_time, out=y[:, :, ph::2, pw::2, :],
-                          weight_key=f"{name}.phase{ph}{pw}.weight", ref_taps=27)
-        return Act(y)
+                r = self.conv(a, name, kernel=(3, 2, 2), pads=(tp, (1, 0) if ph == 0 else (0, 1), (1, 0) if pw == 0 else (0, 1)),
+                              pad_t=pad_t, pad_hw=pad_hw, up_time=up_time, out=y[:, :, ph::2, pw::2, :],
+                              weight_key=f"{name}.phase{ph}{pw}.weight", ref_taps=27, stats=stats,
+                              want_stats=(ph == 0 and pw == 0))
+                stats = r.stats
+        return Act(y, stats=stats)

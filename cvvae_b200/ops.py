@@ -93,7 +93,8 @@ class CudaOps:
              stride=(1, 1, 1), offset=(0, 0, 0), pad_t=L.PAD_ZERO, pad_hw=L.PAD_ZERO, up_time=1,
              residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
              out_f32: bool = False, bias_along_m: bool = False, w_ld: int = 0, cout: Optional[int] = None,
-             force: Optional[str] = None, ref_taps: Optional[int] = None) -> torch.Tensor:
+             force: Optional[str] = None, ref_taps: Optional[int] = None, gn_stats: Optional[torch.Tensor] = None,
+             gn_groups: int = 32) -> torch.Tensor:
         """y = alpha * conv(x, w) + bias + residual.  ``w`` is packed [taps, Cout, Cin(ld)]."""
         B, T, H, W, Ci = x.shape
         kt, kh, kw = kernel
@@ -121,6 +122,10 @@ class CudaOps:
         d.dtype = dtype_code(x.dtype)
         d.flags = (L.CONV_BIAS_ALONG_M if bias_along_m else 0) | (L.CONV_OUT_F32 if out_f32 else 0)
         d.alpha = alpha
+        if gn_stats is not None:  # fp64 [B, groups, 2], zeroed by the caller; the epilogue accumulates into it
+            assert gn_stats.dtype == torch.float64 and gn_stats.is_contiguous()
+            d.gn_stats = gn_stats.data_ptr()
+            d.gn_groups = gn_groups
         if residual is not None:
             assert residual.shape == out.shape and residual.stride() == out.stride(), "residual must share y's geometry"
         fn = {None: self.lib.cvvae_conv3d, "tc": self.lib.cvvae_conv3d_tc, "direct": self.lib.cvvae_conv3d_direct}[force]
@@ -143,17 +148,26 @@ class CudaOps:
         return out
 
     # ------------------------------------------------------------------ normalisation
+    def new_stats(self, B: int, groups: int, device) -> torch.Tensor:
+        """Zeroed fp64 [B, groups, 2] accumulator for statistics produced by conv epilogues."""
+        return torch.zeros((B, groups, 2), dtype=torch.float64, device=device)
+
     def groupnorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *,
-                  per_frame: bool = False, silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  per_frame: bool = False, silu: bool = True, out: Optional[torch.Tensor] = None,
+                  stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`stats`: sums already produced by the conv that wrote x (skips the statistics pass)."""
         B, T = x.shape[0], x.shape[1]
         units = B * T if per_frame else B
-        stats = torch.empty((units, groups, 2), dtype=torch.float64, device=x.device)
         if out is None:
             out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
         dt = dtype_code(x.dtype)
         xs, ys = _t5(x), _t5(out)
-        L.check(self.lib.cvvae_groupnorm_stats(C.byref(xs), groups, int(per_frame), stats.data_ptr(), dt, _stream(x)),
-                "cvvae_groupnorm_stats")
+        if stats is None:
+            stats = torch.empty((units, groups, 2), dtype=torch.float64, device=x.device)
+            L.check(self.lib.cvvae_groupnorm_stats(C.byref(xs), groups, int(per_frame), stats.data_ptr(), dt, _stream(x)),
+                    "cvvae_groupnorm_stats")
+        else:
+            assert not per_frame and tuple(stats.shape) == (units, groups, 2)
         L.check(self.lib.cvvae_groupnorm_apply(C.byref(xs), C.byref(ys), groups, int(per_frame), stats.data_ptr(),
                                                gamma.data_ptr(), beta.data_ptr(), eps, int(silu), dt, _stream(x)),
                 "cvvae_groupnorm_apply")

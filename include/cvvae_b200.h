@@ -85,6 +85,10 @@ typedef struct cvvae_conv_desc {
   int32_t dtype;            /* CVVAE_F16 / CVVAE_BF16 */
   int32_t flags;            /* CVVAE_CONV_* */
   float alpha;
+  double* gn_stats;         /* optional [B][gn_groups][2] (sum, sum of squares of the STORED 16-bit y), accumulated:
+                               GroupNorm statistics of the consumer, produced in the conv epilogue instead of a
+                               separate pass over y.  The caller zeroes it (several launches may add to it).  */
+  int32_t gn_groups;
 } cvvae_conv_desc;
 
 /* Dispatcher: tcgen05 implicit-GEMM kernel when eligible (x.s_c==1, Cin%8==0, 16B-aligned strides,

@@ -45,7 +45,7 @@ class FakeOps:
 
     def conv(self, x, w, bias, *, kernel=(1, 1, 1), stride=(1, 1, 1), offset=(0, 0, 0), pad_t=PAD_ZERO, pad_hw=PAD_ZERO,
              up_time=1, residual=None, alpha=1.0, out=None, out_f32=False, bias_along_m=False, w_ld=0, cout=None,
-             force=None, ref_taps=None):
+             force=None, ref_taps=None, gn_stats=None, gn_groups=32):
         self.launches += 1
         assert out is not None
         kt, kh, kw = kernel
@@ -97,16 +97,35 @@ class FakeOps:
         if residual is not None:
             y = y + residual.to(self.cd)
         out.copy_(y.to(out.dtype))
+        if gn_stats is not None:  # sums of the STORED values per (sample, group)
+            v = out.to(torch.float64)
+            Bc, Tc, Hc, Wc, Cc = v.shape
+            g = v.reshape(Bc, Tc * Hc * Wc, gn_groups, Cc // gn_groups)
+            gn_stats[:, :, 0] += g.sum(dim=(1, 3))
+            gn_stats[:, :, 1] += (g * g).sum(dim=(1, 3))
         return out
 
+    def new_stats(self, B, groups, device):
+        return torch.zeros((B, groups, 2), dtype=torch.float64, device=device)
+
     # ---- norms
-    def groupnorm(self, x, gamma, beta, groups, eps, *, per_frame=False, silu=True, out=None):
+    def groupnorm(self, x, gamma, beta, groups, eps, *, per_frame=False, silu=True, out=None, stats=None):
         self.launches += 2
         B, T, H, W, Cc = x.shape
         xin = _ncdhw(x).to(self.cd)
         if per_frame:
             xin = xin.permute(0, 2, 1, 3, 4).reshape(B * T, Cc, H, W)
-        y = F.group_norm(xin, groups, gamma.to(self.cd), beta.to(self.cd), eps)
+        if stats is not None:
+            # statistics handed over by the producing conv: normalise with exactly those sums
+            cnt = T * H * W * (Cc // groups)
+            mean = (stats[:, :, 0] / cnt)
+            var = (stats[:, :, 1] / cnt - mean * mean).clamp_min(0)
+            rstd = (var + eps).rsqrt()
+            mean_c = mean.repeat_interleave(Cc // groups, dim=1).to(self.cd).view(B, Cc, 1, 1, 1)
+            rstd_c = rstd.repeat_interleave(Cc // groups, dim=1).to(self.cd).view(B, Cc, 1, 1, 1)
+            y = (xin - mean_c) * rstd_c * gamma.to(self.cd).view(1, -1, 1, 1, 1) + beta.to(self.cd).view(1, -1, 1, 1, 1)
+        else:
+            y = F.group_norm(xin, groups, gamma.to(self.cd), beta.to(self.cd), eps)
         if silu:
             y = y * torch.sigmoid(y)
         if per_frame:

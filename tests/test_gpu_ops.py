@@ -248,3 +248,34 @@ def test_data_movement_is_bit_exact():
     assert torch.equal(b1, b2)
     w = _rand((128, 64, 3, 3, 3), torch.float16, 43)
     assert torch.equal(ops.pack_weight(w), fake.pack_weight(w))
+
+
+@pytest.mark.parametrize("name", ["causal333", "frame133_odd", "uptime", "wide512", "res_bias_alpha", "phase322", "cin32"])
+def test_conv_fused_groupnorm_stats(name):
+    """The conv epilogue's (sum, sum^2) per (sample, group) equal those of the tensor it stored."""
+    ops, fake = _ops(), FakeOps()
+    xs, Co, kernel, stride, pads, pad_t, pad_hw, up_time, ex = CONV_CASES[name]
+    yC = Co // 2 if up_time == 2 else Co
+    stats = ops.new_stats(xs[0], 32, DEV)
+    B, T, H, W, Ci = xs
+    taps = kernel[0] * kernel[1] * kernel[2]
+    x = _rand(xs, torch.float16, 3)
+    w = _rand((taps, Co, Ci), torch.float16, 4, scale=(taps * Ci) ** -0.5 * 2)
+    bias = _rand((Co,), torch.float32, 5, 0.3)
+    (tl, th), (hl, hh), (wl, wh) = pads
+    To = (T + tl + th - kernel[0]) // stride[0] + 1
+    Ho = (H + hl + hh - kernel[1]) // stride[1] + 1
+    Wo = (W + wl + wh - kernel[2]) // stride[2] + 1
+    yshape = (B, 2 * To - 1, Ho, Wo, yC) if up_time == 2 else (B, To, Ho, Wo, Co)
+    y = torch.zeros(yshape, dtype=torch.float16, device=DEV)
+    ops.conv(x, w, bias, kernel=kernel, stride=stride, offset=(-tl, -hl, -wl), pad_t=pad_t, pad_hw=pad_hw, up_time=up_time,
+             out=y, gn_stats=stats, gn_groups=32)
+    torch.cuda.synchronize()
+    v = y.double().reshape(B, -1, 32, yC // 32)
+    want = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
+    torch.testing.assert_close(stats, want, rtol=1e-5, atol=1e-3)
+    # and GroupNorm fed with them equals GroupNorm computing its own
+    g = _rand((yC,), torch.float32, 21) * 0.5 + 1.0
+    b = _rand((yC,), torch.float32, 22, 0.2)
+    torch.testing.assert_close(ops.groupnorm(y, g, b, 32, 1e-5, stats=stats).float(), ops.groupnorm(y, g, b, 32, 1e-5).float(),
+                               rtol=1e-3, atol=1e-3)
