@@ -20,6 +20,8 @@
 //
 // Replaces cuDNN behind CausalConv3d / nn.Conv3d / Conv2dWithExtraDim / Downsample3D / Upsample3D
 // (reference: models/vae_models.py:198-340, models/vae_blocks3d_sd3.py:16-364); see include/cvvae_b200.h.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -33,6 +35,7 @@ struct ConvTcParams {
   // tiling
   int TW, ROWS, NACC, TH, N_cta, KHs, n_hgroups, slab_rows;
   int tiles_w, tiles_h, n_tiles_n, cblocks, flat;
+  int tiles_hp;  // h-tiles per grid column: tiles_h, or ceil(tiles_h / 2) CTA pairs with cta_group::2
   int NA, NB;
   uint32_t slab_bytes, b_bytes, idesc;
   // epilogue
@@ -57,8 +60,9 @@ struct TileCoord {
   int b, t, h0, w0, n0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p) {
-  int id = blockIdx.x;
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int rank) {
+  int id = blockIdx.x / CG;
   TileCoord c;
   c.n0 = (id % p.n_tiles_n) * p.N_cta;
   id /= p.n_tiles_n;
@@ -66,8 +70,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p) {
   id /= p.T_out;
   c.w0 = (id % p.tiles_w) * (p.flat ? p.NACC * 128 : p.TW);
   id /= p.tiles_w;
-  c.h0 = (id % p.tiles_h) * p.TH;
-  c.b = id / p.tiles_h;
+  c.h0 = ((id % p.tiles_hp) * CG + rank) * p.TH;  // the two CTAs of a pair own vertically adjacent tiles
+  c.b = id / p.tiles_hp;
   return c;
 }
 
@@ -87,7 +91,10 @@ __device__ __forceinline__ void for_each_slab(const ConvTcParams& p, int t, F&& 
   }
 }
 
-template <int DT>
+// CG = 1: one CTA per tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) shares every weight tile - each
+// CTA stages half of its rows, the 256 x N MMA reads both halves - which halves the weight traffic from L2 and
+// the tensor core's shared-memory operand reads per FLOP (the N = 128 layers are bound by the latter).
+template <int DT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
@@ -104,25 +111,26 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* accFull = bars + 32;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
   uint64_t* resBar = bars + 40;   // [8] one per warp: residual tile landed (TMA epilogue)
-  float* gn_bins = reinterpret_cast<float*>(bars + 64);  // [64 groups][2] per-CTA partial GroupNorm sums
+  unsigned long long* gn_bins = reinterpret_cast<unsigned long long*>(bars + 64);  // [64 groups][2] fixed-point partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool traced = p.trace != nullptr && static_cast<int>(blockIdx.x) < p.trace_n;
   unsigned long long* trc = traced ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
   if (traced && threadIdx.x == 0) trc[0] = ptx::globaltimer_ns();
-  const TileCoord tc = decode_tile(p);
-  // sub-tiles that contain at least one valid output position
+  const int rank = CG == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const TileCoord tc = decode_tile<CG>(p, rank);
+  // sub-tiles that contain at least one valid output position (0 for the idle half of an odd last pair)
   int nacc_eff;
   if (p.flat) {
     int rem = p.W_out - tc.w0;
     nacc_eff = min(p.NACC, (rem + 127) / 128);
   } else {
     int rem = p.H_out - tc.h0;
-    nacc_eff = min(p.NACC, (rem + p.ROWS - 1) / p.ROWS);
+    nacc_eff = max(0, min(p.NACC, (rem + p.ROWS - 1) / p.ROWS));
   }
 
-  if (threadIdx.x < 128) gn_bins[threadIdx.x] = 0.f;
+  if (threadIdx.x < 128) gn_bins[threadIdx.x] = 0ull;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NA; ++i) {
       ptx::mbar_init(&fullA[i], 1);
@@ -139,11 +147,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     ptx::prefetch_tmap(&tmB);
   }
   if (warp == 3) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();  // the peer's barriers / TMEM exist before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (traced && threadIdx.x == 0) trc[1] = ptx::globaltimer_ns();
@@ -163,6 +176,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             ptx::mbar_expect_tx(&fullA[slot], static_cast<uint32_t>(nacc_eff) * 128u * 128u);
             for (int s = 0; s < nacc_eff; ++s)
               ptx::tma_load_5d(dst + s * 16384, &tmA, &fullA[slot], cb * 64, tc.w0 + s * 128, 0, ti, tc.b);
+          } else if (CG == 2) {
+            // both CTAs' bytes complete on the leader's barrier
+            if (rank == 0) ptx::mbar_expect_tx(&fullA[slot], 2u * p.slab_bytes);
+            ptx::tma_load_5d_cg2(dst, &tmA, ptx::mapa_u32(ptx::smem_u32(&fullA[slot]), 0), cb * 64,
+                                 tc.w0 * p.sw + kw + p.off_w, tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
           } else {
             ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
             ptx::tma_load_5d(dst, &tmA, &fullA[slot], cb * 64, tc.w0 * p.sw + kw + p.off_w,
@@ -186,8 +204,15 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int tap = (kt * p.KH + hg * p.KHs + khs) * p.KW + kw;
           wait_bar(&emptyB[slot], phase ^ 1);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
-            ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
+            if (CG == 2) {
+              // each CTA stages its half of the N_cta weight rows
+              if (rank == 0) ptx::mbar_expect_tx(&fullB[slot], 2u * p.b_bytes);
+              ptx::tma_load_3d_cg2(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, ptx::mapa_u32(ptx::smem_u32(&fullB[slot]), 0),
+                                   cb * 64, tc.n0 + rank * (p.N_cta / 2), tap);
+            } else {
+              ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+              ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
+            }
           }
           __syncwarp();
           if (++slot == p.NB) {
@@ -197,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       });
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------- MMA issuer
+  } else if (warp == 2 && rank == 0) {
+    // ------------------------------------------------------------- MMA issuer (the pair's leader when CG = 2)
     // Issue rate matters: one UTCHMMA covers only 64 (N=128) / 128 (N=256) tensor-pipe cycles, so the loop
     // around it must stay a handful of uniform-datapath instructions.  All 32 lanes run the control flow
     // (operands provably uniform -> no per-instruction ELECT/broadcast sequences), descriptors are a
@@ -233,7 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int s = 0; s < nacc_eff; ++s) {
               const uint32_t a_lo = a_lo1 + static_cast<uint32_t>(s) * sub_stride16;
               const uint32_t d = tmem_base + static_cast<uint32_t>(s) * ncta;
-              if (ksteps == 4) {
+              if (CG == 2) {
+                for (int k = 0; k < ksteps; ++k)
+                  ptx::umma_f16_lohi_cg2(d, a_lo + 2 * k, b_lo0 + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+              } else if (ksteps == 4) {
                 ptx::umma_f16_lohi(d, a_lo, b_lo0, kDescHi, idesc, accumulate);
                 ptx::umma_f16_lohi(d, a_lo + 2, b_lo0 + 2, kDescHi, idesc, 1);
                 ptx::umma_f16_lohi(d, a_lo + 4, b_lo0 + 4, kDescHi, idesc, 1);
@@ -243,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                   ptx::umma_f16_lohi(d, a_lo + 2 * k, b_lo0 + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
               }
             }
-            ptx::umma_commit(&emptyB[slotB]);
+            if (CG == 2) ptx::umma_commit_pair(&emptyB[slotB]); else ptx::umma_commit(&emptyB[slotB]);
           }
           __syncwarp();
           accumulate = 1;
@@ -252,14 +280,18 @@ __global__ void __launch_bounds__(kThreads, 1)
             phaseB ^= 1;
           }
         }
-        if (ptx::elect_one()) ptx::umma_commit(&emptyA[slotA]);
+        if (ptx::elect_one()) {
+          if (CG == 2) ptx::umma_commit_pair(&emptyA[slotA]); else ptx::umma_commit(&emptyA[slotA]);
+        }
         __syncwarp();
         if (++slotA == p.NA) {
           slotA = 0;
           phaseA ^= 1;
         }
       });
-      if (ptx::elect_one()) ptx::umma_commit(accFull);
+      if (ptx::elect_one()) {
+        if (CG == 2) ptx::umma_commit_pair(accFull); else ptx::umma_commit(accFull);
+      }
       __syncwarp();
       if (traced && lane == 0) trc[4] = ptx::globaltimer_ns();
     }
@@ -411,15 +443,15 @@ __global__ void __launch_bounds__(kThreads, 1)
               }
               const int lanes_per_group = min(p.gn_cpg >> 1, 32);
               if ((lane % lanes_per_group) == 0 && ch < p.yC) {
-                atomicAdd(&gn_bins[(ch / p.gn_cpg) * 2], ts);
-                atomicAdd(&gn_bins[(ch / p.gn_cpg) * 2 + 1], tq);
+                atomicAdd(&gn_bins[(ch / p.gn_cpg) * 2], gn_fix(ts, kGnSumScale));
+                atomicAdd(&gn_bins[(ch / p.gn_cpg) * 2 + 1], gn_fix(tq, kGnSqScale));
               }
             } else if (ch < p.yC) {  // one channel per group
-              atomicAdd(&gn_bins[ch * 2], s0);
-              atomicAdd(&gn_bins[ch * 2 + 1], q0);
+              atomicAdd(&gn_bins[ch * 2], gn_fix(s0, kGnSumScale));
+              atomicAdd(&gn_bins[ch * 2 + 1], gn_fix(q0, kGnSqScale));
               if (ch + 1 < p.yC) {
-                atomicAdd(&gn_bins[(ch + 1) * 2], s1);
-                atomicAdd(&gn_bins[(ch + 1) * 2 + 1], q1);
+                atomicAdd(&gn_bins[(ch + 1) * 2], gn_fix(s1, kGnSumScale));
+                atomicAdd(&gn_bins[(ch + 1) * 2 + 1], gn_fix(q1, kGnSqScale));
               }
             }
           }
@@ -555,14 +587,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (traced && threadIdx.x == 128) trc[6] = ptx::globaltimer_ns();
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();  // the leader's MMAs wrote the peer's TMEM too
   if (p.gn_stats && static_cast<int>(threadIdx.x) < 2 * p.gn_groups) {
-    const float vsum = gn_bins[threadIdx.x];
-    if (vsum != 0.f) atomicAdd(p.gn_stats + static_cast<size_t>(tc.b) * 2 * p.gn_groups + threadIdx.x, static_cast<double>(vsum));
+    const unsigned long long vsum = gn_bins[threadIdx.x];
+    if (vsum != 0ull)
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_stats) + static_cast<size_t>(tc.b) * 2 * p.gn_groups + threadIdx.x, vsum);
   }
   if (warp == 3) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
     if (traced && lane == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -712,11 +745,18 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     p.tiles_h = (p.H_out + p.TH - 1) / p.TH;
   }
   p.slab_bytes = p.flat ? static_cast<uint32_t>(p.NACC) * 16384u : static_cast<uint32_t>(p.slab_rows * p.TW) * 128u;
-  p.b_bytes = static_cast<uint32_t>(N_cta) * 128u;
-  p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128, N_cta);
+  // CTA pairs (cta_group::2) when there are at least two vertically adjacent tiles to pair up
+  static const int cg_env = [] {
+    const char* e = getenv("CVVAE_CONV_CTA_GROUP");
+    return e ? atoi(e) : 0;
+  }();
+  const int CG = (cg_env == 1 || p.flat || p.tiles_h < 2 || N_cta < 32) ? 1 : 2;
+  p.tiles_hp = (p.tiles_h + CG - 1) / CG;
+  p.b_bytes = static_cast<uint32_t>(N_cta / CG) * 128u;  // weight rows staged per CTA
+  p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128 * CG, N_cta);
 
   // ---- shared memory budget: 227 KB - alignment slack - barriers
-  const size_t budget = 232448 - 1024 - 1024;
+  const size_t budget = 232448 - 1024 - 1536;
   int NB = 4;
   while (NB > 2 && static_cast<size_t>(NB) * p.b_bytes + 2ull * p.slab_bytes > budget) --NB;
   size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;
@@ -727,7 +767,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_bytes <= budget) ++NB;
   p.NA = NA;
   p.NB = NB;
-  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 1024;
+  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 1536;
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
@@ -753,7 +793,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)taps};
     const cuuint64_t wld = d->w_ld ? (cuuint64_t)d->w_ld : (cuuint64_t)p.Cin;
     cuuint64_t strides[2] = {wld * 2, wld * p.Cout * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)N_cta, 1}, estr[3] = {1, 1, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)(N_cta / CG), 1}, estr[3] = {1, 1, 1};
     if (!encode_map(&tmB, d->w, 3, dims, strides, box, estr)) return CVVAE_E_CUDA;
   }
 
@@ -792,15 +832,32 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     p.gn_cpg = cpg;
   }
 
-  const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_h * p.B;
+  const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_hp * p.B * CG;
   CVVAE_CHECK_ARG(grid > 0 && grid < (1ll << 31), "conv_tc: grid size %lld out of range", grid);
   CVVAE_DISPATCH_DTYPE(d->dtype, {
     static bool attr_set = false;
     if (!attr_set) {
-      CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
       attr_set = true;
     }
-    conv_tc_kernel<DT><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(tmA, tmB, tmY, tmR, p);
+    if (CG == 2) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(static_cast<unsigned>(grid));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CVVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<DT, 2>, tmA, tmB, tmY, tmR, p));
+    } else {
+      conv_tc_kernel<DT, 1><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(tmA, tmB, tmY, tmR, p);
+    }
   });
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;

@@ -34,10 +34,10 @@ __device__ __forceinline__ long long gn_offset(long long pix, int unit_t, int pe
 }
 
 template <int DT>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const GnView v, double* __restrict__ stats) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const GnView v, unsigned long long* __restrict__ stats) {
   using E = Elem<DT>;
-  __shared__ double s_sum[64];
-  __shared__ double s_sq[64];
+  __shared__ unsigned long long s_sum[64];
+  __shared__ unsigned long long s_sq[64];
   const int unit = blockIdx.y;  // b or b*T+t
   const int b = v.per_frame ? unit / v.T : unit;
   const int ut = v.per_frame ? unit % v.T : 0;
@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnView v, double* _
   const int pl = threadIdx.x / vecs;
   const int cpg = v.C / v.groups;
   if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0.0;
-    s_sq[threadIdx.x] = 0.0;
+    s_sum[threadIdx.x] = 0ull;
+    s_sq[threadIdx.x] = 0ull;
   }
   __syncthreads();
   const long long p0 = static_cast<long long>(blockIdx.x) * v.pix_per_block;
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnView v, double* _
         tq += q[j];
       }
       const int g = (vec * 8) / cpg;
-      atomicAdd(&s_sum[g], static_cast<double>(ts));
-      atomicAdd(&s_sq[g], static_cast<double>(tq));
+      atomicAdd(&s_sum[g], gn_fix(ts, kGnSumScale));
+      atomicAdd(&s_sq[g], gn_fix(tq, kGnSqScale));
     } else {
       for (int j0 = 0; j0 < 8; j0 += cpg) {
         float ts = 0.f, tq = 0.f;
@@ -115,21 +115,21 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnView v, double* _
           tq += q[j];
         }
         const int g = (vec * 8 + j0) / cpg;
-        atomicAdd(&s_sum[g], static_cast<double>(ts));
-        atomicAdd(&s_sq[g], static_cast<double>(tq));
+        atomicAdd(&s_sum[g], gn_fix(ts, kGnSumScale));
+        atomicAdd(&s_sq[g], gn_fix(tq, kGnSqScale));
       }
     }
   }
   __syncthreads();
   if (threadIdx.x < v.groups) {
-    double* o = stats + (static_cast<long long>(unit) * v.groups + threadIdx.x) * 2;
+    unsigned long long* o = stats + (static_cast<long long>(unit) * v.groups + threadIdx.x) * 2;
     atomicAdd(o, s_sum[threadIdx.x]);
     atomicAdd(o + 1, s_sq[threadIdx.x]);
   }
 }
 
 template <int DT>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const long long* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int silu) {
   using E = Elem<DT>;
@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const dou
   const double cnt = static_cast<double>(v.pix_per_unit) * cpg;
   for (int c = threadIdx.x; c < v.C; c += blockDim.x) {
     const int g = c / cpg;
-    const double sum = stats[(static_cast<long long>(unit) * v.groups + g) * 2];
-    const double sq = stats[(static_cast<long long>(unit) * v.groups + g) * 2 + 1];
+    const double sum = static_cast<double>(stats[(static_cast<long long>(unit) * v.groups + g) * 2]) / kGnSumScale;
+    const double sq = static_cast<double>(stats[(static_cast<long long>(unit) * v.groups + g) * 2 + 1]) / kGnSqScale;
     const double mean = sum / cnt;
     double var = sq / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -343,7 +343,7 @@ int cvvae::gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_fram
   if (zero_first) CVVAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * units, stream));
   dim3 grid;
   pick_grid(v, units, grid);
-  CVVAE_DISPATCH_DTYPE(dtype, { gn_stats_kernel<DT><<<grid, 256, 0, stream>>>(v, stats); });
+  CVVAE_DISPATCH_DTYPE(dtype, { gn_stats_kernel<DT><<<grid, 256, 0, stream>>>(v, reinterpret_cast<unsigned long long*>(stats)); });
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;
 }
@@ -360,7 +360,7 @@ extern "C" int cvvae_groupnorm_apply(const cvvae_tensor5* x, const cvvae_tensor5
   dim3 grid;
   pick_grid(v, units, grid);
   const size_t smem = sizeof(float) * 2 * x->C;
-  CVVAE_DISPATCH_DTYPE(dtype, { gn_apply_kernel<DT><<<grid, 256, smem, stream>>>(v, stats, gamma, beta, eps, silu); });
+  CVVAE_DISPATCH_DTYPE(dtype, { gn_apply_kernel<DT><<<grid, 256, smem, stream>>>(v, reinterpret_cast<const long long*>(stats), gamma, beta, eps, silu); });
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;
 }

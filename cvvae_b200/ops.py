@@ -123,7 +123,7 @@ class CudaOps:
         d.flags = (L.CONV_BIAS_ALONG_M if bias_along_m else 0) | (L.CONV_OUT_F32 if out_f32 else 0)
         d.alpha = alpha
         if gn_stats is not None:  # fp64 [B, groups, 2], zeroed by the caller; the epilogue accumulates into it
-            assert gn_stats.dtype == torch.float64 and gn_stats.is_contiguous()
+            assert gn_stats.dtype == torch.int64 and gn_stats.is_contiguous()
             d.gn_stats = gn_stats.data_ptr()
             d.gn_groups = gn_groups
         if residual is not None:
@@ -149,8 +149,8 @@ class CudaOps:
 
     # ------------------------------------------------------------------ normalisation
     def new_stats(self, B: int, groups: int, device) -> torch.Tensor:
-        """Zeroed fp64 [B, groups, 2] accumulator for statistics produced by conv epilogues."""
-        return torch.zeros((B, groups, 2), dtype=torch.float64, device=device)
+        """Zeroed int64 fixed-point [B, groups, 2] accumulator (sum * 2^20, sum^2 * 2^18) for conv-epilogue statistics."""
+        return torch.zeros((B, groups, 2), dtype=torch.int64, device=device)
 
     def groupnorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *,
                   per_frame: bool = False, silu: bool = True, out: Optional[torch.Tensor] = None,
@@ -163,7 +163,7 @@ class CudaOps:
         dt = dtype_code(x.dtype)
         xs, ys = _t5(x), _t5(out)
         if stats is None:
-            stats = torch.empty((units, groups, 2), dtype=torch.float64, device=x.device)
+            stats = torch.empty((units, groups, 2), dtype=torch.int64, device=x.device)
             L.check(self.lib.cvvae_groupnorm_stats(C.byref(xs), groups, int(per_frame), stats.data_ptr(), dt, _stream(x)),
                     "cvvae_groupnorm_stats")
         else:

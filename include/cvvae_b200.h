@@ -85,7 +85,7 @@ typedef struct cvvae_conv_desc {
   int32_t dtype;            /* CVVAE_F16 / CVVAE_BF16 */
   int32_t flags;            /* CVVAE_CONV_* */
   float alpha;
-  double* gn_stats;         /* optional [B][gn_groups][2] (sum, sum of squares of the STORED 16-bit y), accumulated:
+  double* gn_stats;         /* optional [B][gn_groups][2] int64 fixed point as above (of the STORED 16-bit y), accumulated:
                                GroupNorm statistics of the consumer, produced in the conv epilogue instead of a
                                separate pass over y.  The caller zeroes it (several launches may add to it).  */
   int32_t gn_groups;
@@ -108,7 +108,8 @@ int cvvae_pack_conv_weight(const void* w_oikkk, void* w_packed, int32_t Cout, in
  * 392-401) and nn.GroupNorm+nn.SiLU of the sd3 blocks.  Statistics over (C/groups, T, H, W) per
  * sample; pass per_frame=1 for the attention blocks, whose GroupNorm sees T folded into the batch
  * (models/vae_models.py:466,533,622).
- *   stats workspace: fp64 [B*(per_frame?T:1)][groups][2]  (sum, sum of squares); zeroed by the call.
+ *   stats workspace: int64 [B*(per_frame?T:1)][groups][2] FIXED POINT (sum * 2^20, sum of squares * 2^18): integer
+ *   atomics make the accumulation order-independent, hence bit-reproducible; zeroed by cvvae_groupnorm_stats.
  */
 int cvvae_groupnorm_stats(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats,
                           int32_t dtype, void* stream);

@@ -16,6 +16,7 @@ import torch
 import torch.nn.functional as F
 
 PAD_ZERO, PAD_REPLICATE = 0, 1
+GN_SUM_SCALE, GN_SQ_SCALE = 2.0 ** 20, 2.0 ** 18  # fixed-point statistics format of the C ABI
 
 
 def _ncdhw(x):  # logical [B,T,H,W,C] -> [B,C,T,H,W]
@@ -101,12 +102,12 @@ class FakeOps:
             v = out.to(torch.float64)
             Bc, Tc, Hc, Wc, Cc = v.shape
             g = v.reshape(Bc, Tc * Hc * Wc, gn_groups, Cc // gn_groups)
-            gn_stats[:, :, 0] += g.sum(dim=(1, 3))
-            gn_stats[:, :, 1] += (g * g).sum(dim=(1, 3))
+            gn_stats[:, :, 0] += torch.round(g.sum(dim=(1, 3)) * GN_SUM_SCALE).to(torch.int64)
+            gn_stats[:, :, 1] += torch.round((g * g).sum(dim=(1, 3)) * GN_SQ_SCALE).to(torch.int64)
         return out
 
     def new_stats(self, B, groups, device):
-        return torch.zeros((B, groups, 2), dtype=torch.float64, device=device)
+        return torch.zeros((B, groups, 2), dtype=torch.int64, device=device)
 
     # ---- norms
     def groupnorm(self, x, gamma, beta, groups, eps, *, per_frame=False, silu=True, out=None, stats=None):
@@ -118,8 +119,8 @@ class FakeOps:
         if stats is not None:
             # statistics handed over by the producing conv: normalise with exactly those sums
             cnt = T * H * W * (Cc // groups)
-            mean = (stats[:, :, 0] / cnt)
-            var = (stats[:, :, 1] / cnt - mean * mean).clamp_min(0)
+            mean = (stats[:, :, 0].double() / GN_SUM_SCALE / cnt)
+            var = (stats[:, :, 1].double() / GN_SQ_SCALE / cnt - mean * mean).clamp_min(0)
             rstd = (var + eps).rsqrt()
             mean_c = mean.repeat_interleave(Cc // groups, dim=1).to(self.cd).view(B, Cc, 1, 1, 1)
             rstd_c = rstd.repeat_interleave(Cc // groups, dim=1).to(self.cd).view(B, Cc, 1, 1, 1)

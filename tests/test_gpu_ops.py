@@ -95,6 +95,15 @@ CONV_CASES = {
                     {"lattice_out": (0, 1)}),
     "phase322": ((1, 2, 20, 16, 128), 256, (3, 2, 2), (1, 1, 1), ((1, 1), (0, 1), (1, 0)), PAD_REPLICATE, PAD_ZERO, 1,
                  {"lattice_out": (1, 0)}),
+    # tall enough for CTA pairs (cta_group::2): even / odd number of row tiles, strided, interleaved, residual
+    "pair_n128": ((1, 3, 80, 48, 64), 128, (3, 3, 3), (1, 1, 1), ((2, 0), (1, 1), (1, 1)), PAD_REPLICATE, PAD_ZERO, 1, {}),
+    "pair_n256_odd": ((1, 2, 72, 40, 128), 256, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1,
+                      {"residual": True}),
+    "pair_n512": ((1, 2, 50, 33, 256), 512, (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
+    "pair_down": ((1, 5, 130, 66, 128), 128, (3, 3, 3), (2, 2, 2), ((2, 0), (0, 1), (0, 1)), PAD_REPLICATE, PAD_ZERO, 1, {}),
+    "pair_phase_up": ((1, 3, 70, 24, 128), 256, (3, 2, 2), (1, 1, 1), ((1, 1), (1, 0), (0, 1)), PAD_REPLICATE, PAD_ZERO, 2,
+                      {"lattice_out": (0, 1)}),
+    "pair_cout32": ((1, 2, 90, 20, 64), 32, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
     "conv1x1_spatial": ((1, 2, 20, 20, 128), 256, (1, 1, 1), (1, 1, 1), ((0, 0), (0, 0), (0, 0)), PAD_ZERO, PAD_ZERO, 1,
                         {"strided_in": True}),
 }
@@ -250,7 +259,8 @@ def test_data_movement_is_bit_exact():
     assert torch.equal(ops.pack_weight(w), fake.pack_weight(w))
 
 
-@pytest.mark.parametrize("name", ["causal333", "frame133_odd", "uptime", "wide512", "res_bias_alpha", "phase322", "cin32"])
+@pytest.mark.parametrize("name", ["causal333", "frame133_odd", "uptime", "wide512", "res_bias_alpha", "phase322", "cin32",
+                                  "pair_n128", "pair_n256_odd", "pair_phase_up"])
 def test_conv_fused_groupnorm_stats(name):
     """The conv epilogue's (sum, sum^2) per (sample, group) equal those of the tensor it stored."""
     ops, fake = _ops(), FakeOps()
@@ -273,7 +283,8 @@ def test_conv_fused_groupnorm_stats(name):
     torch.cuda.synchronize()
     v = y.double().reshape(B, -1, 32, yC // 32)
     want = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
-    torch.testing.assert_close(stats, want, rtol=1e-5, atol=1e-3)
+    got = torch.stack([stats[..., 0].double() / 2.0 ** 20, stats[..., 1].double() / 2.0 ** 18], dim=-1)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-2)
     # and GroupNorm fed with them equals GroupNorm computing its own
     g = _rand((yC,), torch.float32, 21) * 0.5 + 1.0
     b = _rand((yC,), torch.float32, 22, 0.2)
