@@ -750,7 +750,11 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     const char* e = getenv("CVVAE_CONV_CTA_GROUP");
     return e ? atoi(e) : 0;
   }();
-  const int CG = (cg_env == 1 || p.flat || p.tiles_h < 2 || N_cta < 32) ? 1 : 2;
+  // measured (tools/bench_conv.py): pairs help the N_cta = 256 layers (half the weight bytes per CTA, up to +10 %)
+  // and cost 0-16 % on the N_cta = 128 layers, so they are on for N_cta = 256 only (CVVAE_CONV_CTA_GROUP=2 forces them
+  // wherever possible, =1 switches them off)
+  const bool pair_ok = !p.flat && p.tiles_h >= 2 && N_cta >= 32;
+  const int CG = (cg_env == 1 || !pair_ok) ? 1 : ((cg_env == 2 || N_cta == 256) ? 2 : 1);
   p.tiles_hp = (p.tiles_h + CG - 1) / CG;
   p.b_bytes = static_cast<uint32_t>(N_cta / CG) * 128u;  // weight rows staged per CTA
   p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128 * CG, N_cta);

@@ -174,14 +174,22 @@ class Engine:
         yC = yshape[4]
         cpg = yC // self.cfg.groups if yC % self.cfg.groups == 0 else 0
         stats_ok = (cpg >= 1 and (cpg & (cpg - 1)) == 0 and out.stride(4) == 1 and yC % 8 == 0
-                    and all(st_ % 8 == 0 for st_ in out.stride()[:4]) and (not flat or B == 1))
+                    and all(st_ % 8 == 0 for st_ in out.stride()[:4]))
         if (want_stats or stats is not None) and stats_ok:
             if stats is None:
                 stats = self.ops.new_stats(B, self.cfg.groups, x.device)
         else:
             stats = None
         skw = dict(gn_stats=stats, gn_groups=self.cfg.groups) if stats is not None else {}
-        if flat:
+        if flat and stats is not None and B > 1:
+            # one flat GEMM per sample so that the epilogue's GroupNorm sums stay per sample (and results do not
+            # depend on how many clips share a batch)
+            P = T * H * W
+            for bi in range(B):
+                self.ops.conv(x[bi].view(1, 1, 1, P, x.shape[4]), w, b, kernel=kernel,
+                              residual=residual[bi].view(1, 1, 1, P, Co) if residual is not None else None,
+                              out=out[bi].view(1, 1, 1, P, Co), gn_stats=stats[bi:bi + 1], gn_groups=self.cfg.groups)
+        elif flat:
             P = B * T * H * W
             xf = x.view(1, 1, 1, P, x.shape[4])
             of = out.view(1, 1, 1, P, Co)

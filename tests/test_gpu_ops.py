@@ -290,3 +290,15 @@ def test_conv_fused_groupnorm_stats(name):
     b = _rand((yC,), torch.float32, 22, 0.2)
     torch.testing.assert_close(ops.groupnorm(y, g, b, 32, 1e-5, stats=stats).float(), ops.groupnorm(y, g, b, 32, 1e-5).float(),
                                rtol=1e-3, atol=1e-3)
+
+
+def test_conv_pairs_forced_everywhere():
+    """CTA pairs are enabled by default only where they pay (N_cta = 256); re-run the conv cases with
+    CVVAE_CONV_CTA_GROUP=2 (pairs wherever two row tiles exist) in a fresh process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CVVAE_CONV_CTA_GROUP="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "test_conv_tc_matches_spec or test_conv_fused_groupnorm_stats"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
