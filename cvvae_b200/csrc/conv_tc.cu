@@ -46,6 +46,7 @@ struct ConvTcParams {
   int yC, yT, vec_ok, bias_vec;
   double* gn_stats;  // fused GroupNorm statistics of y (TMA epilogue only)
   int gn_groups, gn_cpg;
+  int swap;  // operands swapped: A = weights (M = 128 output channels), B = 256 positions (Cout == 128 layers)
   int tma_epi, box_w;  // epilogue through swizzled smem + TMA store (box_w = min(TW, 32) positions per box row)
   unsigned long long* trace;  // optional [trace_n][8] globaltimer stamps per CTA (diagnostics)
   int trace_n;
@@ -254,7 +255,20 @@ __global__ void __launch_bounds__(kThreads, 1)
           first = false;
           const uint32_t b_lo0 = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
           const uint32_t a_lo1 = a_lo0 + static_cast<uint32_t>(khs) * tap_stride16;
-          if (ptx::elect_one()) {
+          if (p.swap) {
+            // D[channel lane][position column]: the weight tile is the M = 128 operand, 256 consecutive slab rows
+            // (two 128-position sub-tiles) the N operand -> 4 KB + 8 KB of operand reads per 128-cycle MMA instead of
+            // 4 KB + 4 KB per 64-cycle MMA, which is what bounds the N = 128 orientation
+            if (ptx::elect_one()) {
+              for (int a2 = 0; 2 * a2 < nacc_eff; ++a2) {
+                const uint32_t x_lo = a_lo1 + static_cast<uint32_t>(2 * a2) * sub_stride16;
+                const uint32_t d = tmem_base + static_cast<uint32_t>(a2) * 256u;
+                for (int k = 0; k < ksteps; ++k)
+                  ptx::umma_f16_lohi(d, b_lo0 + 2 * k, x_lo + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+              }
+              ptx::umma_commit(&emptyB[slotB]);
+            }
+          } else if (ptx::elect_one()) {
             for (int s = 0; s < nacc_eff; ++s) {
               const uint32_t a_lo = a_lo1 + static_cast<uint32_t>(s) * sub_stride16;
               const uint32_t d = tmem_base + static_cast<uint32_t>(s) * ncta;
@@ -310,7 +324,81 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (traced && threadIdx.x == 128) trc[5] = ptx::globaltimer_ns();
     const int chalf = p.up_time == 2 ? p.Cout / 2 : p.Cout;
     int item = 0;
-    if (p.tma_epi) {
+    if (p.tma_epi && p.swap) {
+      // ---- swapped orientation: this thread owns output channel c = 32q + lane, a 32x32b TMEM load gives it 32
+      // consecutive positions.  Staging tile = [32 positions][32 channels] (64-byte rows, no swizzle): a warp's 16-bit
+      // stores of one position are 64 contiguous bytes (conflict-free); one TMA store per tile as in the other path.
+      uint8_t* stage = sA + static_cast<size_t>(warp) * 8192;
+      uint32_t res_phase = 0;
+      int nbuf = 0;
+      const int c_me = tc.n0 + q * 32 + lane;
+      const float bias_c = (p.bias && !(p.flags & CVVAE_CONV_BIAS_ALONG_M) && c_me < p.Cout) ? __ldg(p.bias + c_me) : 0.f;
+      float gs = 0.f, gq = 0.f;  // this channel's GroupNorm partial sums over all items of the CTA
+      for (int a2 = 0; 2 * a2 < nacc_eff; ++a2) {
+        for (int j = 0; j < 8; ++j) {
+          const int f0 = a2 * 256 + j * 32;           // first flattened tile position of this item
+          if (f0 >= nacc_eff * 128) break;             // warp-uniform
+          if (((item++) & 1) != grp) continue;         // warp-uniform
+          const int h = tc.h0 + f0 / p.TW, w = tc.w0 + f0 % p.TW;
+          // validity of the 32 positions (lane i <-> position i), shared through a ballot
+          const int hi = tc.h0 + (f0 + lane) / p.TW, wi = tc.w0 + (f0 + lane) % p.TW;
+          const unsigned valid = __ballot_sync(0xffffffffu, (hi < p.H_out) && (wi < p.W_out));
+          uint8_t* tile = stage + (nbuf & 1) * 2048;
+          const uint32_t tile_u32 = ptx::smem_u32(tile);
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          if (p.residual) {
+            if (lane == 0) {
+              ptx::mbar_expect_tx(&resBar[warp], 2048);
+              ptx::tma_load_5d(tile, &tmR, &resBar[warp], tc.n0 + q * 32, w, h, tc.t, tc.b);
+            }
+            wait_bar(&resBar[warp], res_phase);
+            res_phase ^= 1;
+          }
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a2 * 256 + j * 32), v);
+          ptx::tmem_ld_wait();
+          const uint32_t my = tile_u32 + static_cast<uint32_t>(lane) * 2u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = fmaf(__uint_as_float(v[i]), p.alpha, bias_c);
+            if (p.residual) {
+              uint16_t r16;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r16) : "r"(my + i * 64u));
+              a += E::to_f(*reinterpret_cast<const typename E::T*>(&r16));
+            }
+            const typename E::T o = E::from_f(a);
+            if (p.gn_stats && ((valid >> i) & 1u)) {
+              const float of = E::to_f(o);
+              gs += of;
+              gq = fmaf(of, of, gq);
+            }
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(my + i * 64u), "h"(*reinterpret_cast<const uint16_t*>(&o)) : "memory");
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_5d(&tmY, tile, tc.n0 + q * 32, w, h, tc.t, tc.b);
+            ptx::bulk_commit();
+          }
+          ++nbuf;
+        }
+      }
+      if (p.gn_stats) {
+        // channels of one group are neighbouring lanes: reduce over cpg lanes, the first lane of each group adds
+        for (int o = 1; o < p.gn_cpg && o < 32; o <<= 1) {
+          gs += __shfl_xor_sync(0xffffffffu, gs, o);
+          gq += __shfl_xor_sync(0xffffffffu, gq, o);
+        }
+        const int lanes_per_group = min(p.gn_cpg, 32);
+        if ((lane % lanes_per_group) == 0 && c_me < p.yC) {
+          atomicAdd(&gn_bins[(c_me / p.gn_cpg) * 2], gn_fix(gs, kGnSumScale));
+          atomicAdd(&gn_bins[(c_me / p.gn_cpg) * 2 + 1], gn_fix(gq, kGnSqScale));
+        }
+      }
+      if (lane == 0) ptx::bulk_wait<0>();
+      __syncwarp();
+    } else if (p.tma_epi) {
       // ---- TMEM -> registers -> SWIZZLE_128B staging tile (32 positions x 64 channels, 4 KB) -> TMA store.
       // A warp's direct 16-byte stores would touch 32 different 128-byte lines per instruction (position stride
       // = C*2 bytes); the bulk tensor store writes full lines and clips partial tiles by itself.  The residual
@@ -606,14 +694,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // ---------------------------------------------------------------------------------------- host side
 static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                       const cuuint32_t* box, const cuuint32_t* estr) {
+                       const cuuint32_t* box, const cuuint32_t* estr,
+                       CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return false;
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(ptr), dims, strides_b, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
@@ -818,6 +907,19 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
       if (!encode_map(&tmY, y.ptr, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
       if (d->residual && !encode_map(&tmR, d->residual, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
       p.tma_epi = 1;
+      // Cout == 128 layers: swap the MMA operands (see the issue loop) - needs the TMA epilogue's transposing stage
+      static const int swap_env = [] {
+        const char* e = getenv("CVVAE_CONV_SWAP");
+        return e ? atoi(e) : 1;
+      }();
+      p.swap = (swap_env && !p.flat && CG == 1 && p.Cout == 128 && N_cta == 128 && p.NACC == 4 && p.up_time == 1 &&
+                !(d->flags & CVVAE_CONV_BIAS_ALONG_M)) ? 1 : 0;
+      if (p.swap) {
+        cuuint32_t box2[5] = {32, (cuuint32_t)p.box_w, (cuuint32_t)(32 / p.box_w), 1, 1};
+        if (!encode_map(&tmY, y.ptr, 5, dims, strides, box2, estr, CU_TENSOR_MAP_SWIZZLE_NONE)) return CVVAE_E_CUDA;
+        if (d->residual && !encode_map(&tmR, d->residual, 5, dims, strides, box2, estr, CU_TENSOR_MAP_SWIZZLE_NONE)) return CVVAE_E_CUDA;
+        p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128, 256);
+      }
     }
   }
   // fused GroupNorm statistics need the TMA epilogue, power-of-two channels per group and one sample per CTA index
