@@ -300,8 +300,16 @@ def main():
     if prof and prof["conv_tc"]["ms"] > 0:
         tc = prof["conv_tc"]
         achieved = tc["flops"] / (tc["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):  # ncu dram bytes (read + write) per conv_tc launch, from the committed capture of this command
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of the timed region)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": None,
                 "peak_source": peak_src, "algorithmic_tflop_per_step": tc["flops"] / args.steps / 1e12,
                 "kernel_ms_per_step": tc["ms"] / args.steps, "launches_per_step": tc["launches"] / args.steps,
                 "share_of_step": tc["ms"] / ms_total,

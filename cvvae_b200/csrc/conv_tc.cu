@@ -800,6 +800,14 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.N_cta = N_cta;
   p.n_tiles_n = (p.Cout + N_cta - 1) / N_cta;
   p.NACC = (512 / N_cta) < 4 ? (512 / N_cta) : 4;
+  {
+    // experiment knob: fewer accumulators per CTA (halves the reuse of each staged weight tile)
+    static const int nacc_env = [] {
+      const char* e = getenv("CVVAE_CONV_NACC");
+      return e ? atoi(e) : 0;
+    }();
+    if (nacc_env > 0 && nacc_env < p.NACC) p.NACC = nacc_env;
+  }
   p.flat = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1) ? 1 : 0;
   p.cblocks = (p.Cin + 63) / 64;
   if (p.flat) {
@@ -912,7 +920,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
         const char* e = getenv("CVVAE_CONV_SWAP");
         return e ? atoi(e) : 1;
       }();
-      p.swap = (swap_env && !p.flat && CG == 1 && p.Cout == 128 && N_cta == 128 && p.NACC == 4 && p.up_time == 1 &&
+      p.swap = (swap_env && !p.flat && CG == 1 && p.Cout == 128 && N_cta == 128 && (p.NACC == 4 || p.NACC == 2) && p.up_time == 1 &&
                 !(d->flags & CVVAE_CONV_BIAS_ALONG_M)) ? 1 : 0;
       if (p.swap) {
         cuuint32_t box2[5] = {32, (cuuint32_t)p.box_w, (cuuint32_t)(32 / p.box_w), 1, 1};
