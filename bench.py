@@ -309,7 +309,7 @@ def main():
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of the timed region)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": None,
+                "algorithmic_bytes_per_launch": tc["bytes"] / max(tc["launches"], 1),
                 "peak_source": peak_src, "algorithmic_tflop_per_step": tc["flops"] / args.steps / 1e12,
                 "kernel_ms_per_step": tc["ms"] / args.steps, "launches_per_step": tc["launches"] / args.steps,
                 "share_of_step": tc["ms"] / ms_total,

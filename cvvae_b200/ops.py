@@ -53,6 +53,7 @@ class CudaOps:
 
     def start_profile(self):
         self.profile = {"flops": {"conv_tc": 0, "conv_direct": 0}, "ref_flops": {"conv_tc": 0, "conv_direct": 0},
+                        "bytes": {"conv_tc": 0, "conv_direct": 0},
                         "events": {"conv_tc": [], "conv_direct": []}, "launches": {"conv_tc": 0, "conv_direct": 0}}
 
     def stop_profile(self):
@@ -62,7 +63,7 @@ class CudaOps:
         out = {}
         for path in prof["flops"]:
             ms = sum(s.elapsed_time(e) for s, e in prof["events"][path])
-            out[path] = {"flops": prof["flops"][path], "ref_flops": prof["ref_flops"][path], "ms": ms,
+            out[path] = {"flops": prof["flops"][path], "ref_flops": prof["ref_flops"][path], "bytes": prof["bytes"][path], "ms": ms,
                          "launches": prof["launches"][path]}
         return out
 
@@ -139,6 +140,9 @@ class CudaOps:
         mn = 2 * B * t_conv * out.shape[2] * out.shape[3] * Co * Ci
         self.profile["flops"][path] += mn * kt * kh * kw
         self.profile["ref_flops"][path] += mn * (ref_taps if ref_taps is not None else kt * kh * kw)
+        # algorithmic bytes: every operand once (input, weights, residual, output)
+        self.profile["bytes"][path] += (x.numel() * x.element_size() + w.numel() * w.element_size() +
+                                        out.numel() * out.element_size() * (2 if residual is not None else 1))
         self.profile["launches"][path] += 1
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_ev.record()
