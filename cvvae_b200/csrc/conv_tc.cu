@@ -326,44 +326,62 @@ __global__ void __launch_bounds__(kThreads, 1)
     int item = 0;
     if (p.tma_epi && p.swap) {
       // ---- swapped orientation: this thread owns output channel c = 32q + lane, a 32x32b TMEM load gives it 32
-      // consecutive positions.  No staging needed: for each position the warp's 32 lanes write 32 consecutive
-      // channels = one 64-byte segment, so plain 16-bit global stores are already fully coalesced (the residual is
-      // read the same way).  GroupNorm sums accumulate per thread in registers.
+      // consecutive positions.  Staging tile = [32 positions][32 channels] (64-byte rows, no swizzle): a warp's 16-bit
+      // stores of one position are 64 contiguous bytes (conflict-free); one TMA store per tile as in the other path.
+      uint8_t* stage = sA + static_cast<size_t>(warp) * 8192;
+      uint32_t res_phase = 0;
+      int nbuf = 0;
       const int c_me = tc.n0 + q * 32 + lane;
-      const bool c_ok = c_me < p.Cout;
-      const float bias_c = (p.bias && !(p.flags & CVVAE_CONV_BIAS_ALONG_M) && c_ok) ? __ldg(p.bias + c_me) : 0.f;
+      const float bias_c = (p.bias && !(p.flags & CVVAE_CONV_BIAS_ALONG_M) && c_me < p.Cout) ? __ldg(p.bias + c_me) : 0.f;
       float gs = 0.f, gq = 0.f;  // this channel's GroupNorm partial sums over all items of the CTA
-      const int bw_shift = 31 - __clz(p.box_w);  // box_w = min(TW, 32) positions per image row of an item
-      typename E::T* ybase = reinterpret_cast<typename E::T*>(p.y) + tc.b * p.ys_b + tc.t * p.ys_t + c_me;
-      const typename E::T* rbase =
-          p.residual ? reinterpret_cast<const typename E::T*>(p.residual) + tc.b * p.ys_b + tc.t * p.ys_t + c_me : nullptr;
       for (int a2 = 0; 2 * a2 < nacc_eff; ++a2) {
         for (int j = 0; j < 8; ++j) {
           const int f0 = a2 * 256 + j * 32;           // first flattened tile position of this item
           if (f0 >= nacc_eff * 128) break;             // warp-uniform
           if (((item++) & 1) != grp) continue;         // warp-uniform
           const int h = tc.h0 + f0 / p.TW, w = tc.w0 + f0 % p.TW;
+          // validity of the 32 positions (lane i <-> position i), shared through a ballot
+          const int hi = tc.h0 + (f0 + lane) / p.TW, wi = tc.w0 + (f0 + lane) % p.TW;
+          const unsigned valid = __ballot_sync(0xffffffffu, (hi < p.H_out) && (wi < p.W_out));
+          uint8_t* tile = stage + (nbuf & 1) * 2048;
+          const uint32_t tile_u32 = ptx::smem_u32(tile);
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          if (p.residual) {
+            if (lane == 0) {
+              ptx::mbar_expect_tx(&resBar[warp], 2048);
+              ptx::tma_load_5d(tile, &tmR, &resBar[warp], tc.n0 + q * 32, w, h, tc.t, tc.b);
+            }
+            wait_bar(&resBar[warp], res_phase);
+            res_phase ^= 1;
+          }
           uint32_t v[32];
           ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a2 * 256 + j * 32), v);
           ptx::tmem_ld_wait();
-          const long long off0 = h * p.ys_h + w * p.ys_w;
+          const uint32_t my = tile_u32 + static_cast<uint32_t>(lane) * 2u;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int dh = i >> bw_shift, dw = i & (p.box_w - 1);
-            const bool ok = c_ok && (h + dh < p.H_out) && (w + dw < p.W_out);  // warp-uniform apart from c_ok
-            const long long off = off0 + dh * p.ys_h + dw * p.ys_w;
             float a = fmaf(__uint_as_float(v[i]), p.alpha, bias_c);
-            if (rbase && ok) a += E::to_f(__ldg(rbase + off));
-            const typename E::T o = E::from_f(a);
-            if (ok) {
-              ybase[off] = o;
-              if (p.gn_stats) {
-                const float of = E::to_f(o);
-                gs += of;
-                gq = fmaf(of, of, gq);
-              }
+            if (p.residual) {
+              uint16_t r16;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r16) : "r"(my + i * 64u));
+              a += E::to_f(*reinterpret_cast<const typename E::T*>(&r16));
             }
+            const typename E::T o = E::from_f(a);
+            if (p.gn_stats && ((valid >> i) & 1u)) {
+              const float of = E::to_f(o);
+              gs += of;
+              gq = fmaf(of, of, gq);
+            }
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(my + i * 64u), "h"(*reinterpret_cast<const uint16_t*>(&o)) : "memory");
           }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_5d(&tmY, tile, tc.n0 + q * 32, w, h, tc.t, tc.b);
+            ptx::bulk_commit();
+          }
+          ++nbuf;
         }
       }
       if (p.gn_stats) {
@@ -378,6 +396,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           atomicAdd(&gn_bins[(c_me / p.gn_cpg) * 2 + 1], gn_fix(gq, kGnSqScale));
         }
       }
+      if (lane == 0) ptx::bulk_wait<0>();
+      __syncwarp();
     } else if (p.tma_epi) {
       // ---- TMEM -> registers -> SWIZZLE_128B staging tile (32 positions x 64 channels, 4 KB) -> TMA store.
       // A warp's direct 16-byte stores would touch 32 different 128-byte lines per instruction (position stride
@@ -903,6 +923,9 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
       p.swap = (swap_env && !p.flat && CG == 1 && p.Cout == 128 && N_cta == 128 && (p.NACC == 4 || p.NACC == 2) && p.up_time == 1 &&
                 !(d->flags & CVVAE_CONV_BIAS_ALONG_M)) ? 1 : 0;
       if (p.swap) {
+        cuuint32_t box2[5] = {32, (cuuint32_t)p.box_w, (cuuint32_t)(32 / p.box_w), 1, 1};
+        if (!encode_map(&tmY, y.ptr, 5, dims, strides, box2, estr, CU_TENSOR_MAP_SWIZZLE_NONE)) return CVVAE_E_CUDA;
+        if (d->residual && !encode_map(&tmR, d->residual, 5, dims, strides, box2, estr, CU_TENSOR_MAP_SWIZZLE_NONE)) return CVVAE_E_CUDA;
         p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128, 256);
       }
     }
