@@ -46,6 +46,8 @@ struct ConvTcParams {
   int yC, yT, vec_ok, bias_vec;
   double* gn_stats;  // fused GroupNorm statistics of y (TMA epilogue only)
   int gn_groups, gn_cpg;
+  int persist;  // persistent swap kernel: 256-position tiles, two TMEM stages, epilogue overlapped with the next tile
+  int n_tiles;  // tiles of the whole launch (persistent kernel)
   int swap;  // operands swapped: A = weights (M = 128 output channels), B = 256 positions (Cout == 128 layers)
   int tma_epi, box_w;  // epilogue through swizzled smem + TMA store (box_w = min(TW, 32) positions per box row)
   unsigned long long* trace;  // optional [trace_n][8] globaltimer stamps per CTA (diagnostics)
@@ -62,8 +64,8 @@ struct TileCoord {
 };
 
 template <int CG>
-__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int rank) {
-  int id = blockIdx.x / CG;
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int rank, int tile_id = -1) {
+  int id = tile_id >= 0 ? tile_id : static_cast<int>(blockIdx.x) / CG;
   TileCoord c;
   c.n0 = (id % p.n_tiles_n) * p.N_cta;
   id /= p.n_tiles_n;
@@ -692,6 +694,262 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent, operand-swapped variant for the Cout == 128 layers (the full-resolution layers, where a CTA's mainloop is
+// short: 11 us for a 1x3x3 conv).  One CTA per SM walks tiles of 256 output positions; the 128-channel x 256-position
+// accumulator is double buffered in TMEM (2 x 256 columns), so the 8 epilogue warps drain tile i while the MMA warp
+// already runs tile i+1 and the TMA producers prefetch ahead across tile boundaries: set-up, first-load latency and the
+// whole epilogue leave the critical path.  Price: each staged weight tile now feeds one accumulator instead of two.
+// Warps: 0 A producer, 1 B producer, 2 MMA issuer, 3 TMEM allocator, 4-11 epilogue (two per TMEM lane quarter).
+static constexpr int kPersistThreads = 384;
+
+template <int DT>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+    conv_tc_psw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                       const ConvTcParams p) {
+  using E = Elem<DT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + static_cast<size_t>(p.NA) * p.slab_bytes;
+  uint8_t* sStage = sB + static_cast<size_t>(p.NB) * p.b_bytes;  // 8 warps x 2 x 2 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 32768);
+  uint64_t* fullA = bars;          // [8]
+  uint64_t* emptyA = bars + 8;     // [8]
+  uint64_t* fullB = bars + 16;     // [8]
+  uint64_t* emptyB = bars + 24;    // [8]
+  uint64_t* accFull = bars + 32;   // [2]
+  uint64_t* accEmpty = bars + 34;  // [2]
+  uint64_t* resBar = bars + 40;    // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.NA; ++i) {
+      ptx::mbar_init(&fullA[i], 1);
+      ptx::mbar_init(&emptyA[i], 1);
+    }
+    for (int i = 0; i < p.NB; ++i) {
+      ptx::mbar_init(&fullB[i], 1);
+      ptx::mbar_init(&emptyB[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&accFull[i], 1);
+      ptx::mbar_init(&accEmpty[i], 8);  // one arrival per epilogue warp
+    }
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&resBar[i], 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmY);
+  }
+  if (warp == 3) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tile0 = blockIdx.x, tstep = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- A producer (runs ahead across tiles)
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
+      const TileCoord tc = decode_tile<1>(p, 0, tile);
+      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
+        wait_bar(&emptyA[slot], phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
+          ptx::tma_load_5d(sA + static_cast<size_t>(slot) * p.slab_bytes, &tmA, &fullA[slot], cb * 64,
+                           tc.w0 * p.sw + kw + p.off_w, tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
+        }
+        __syncwarp();
+        if (++slot == p.NA) {
+          slot = 0;
+          phase ^= 1;
+        }
+      });
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- B producer
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
+      const TileCoord tc = decode_tile<1>(p, 0, tile);
+      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
+        for (int khs = 0; khs < p.KHs; ++khs) {
+          const int tap = (kt * p.KH + hg * p.KHs + khs) * p.KW + kw;
+          wait_bar(&emptyB[slot], phase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+            ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
+          }
+          __syncwarp();
+          if (++slot == p.NB) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      });
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------- MMA issuer
+    int slotA = 0, slotB = 0;
+    uint32_t phaseA = 0, phaseB = 0;
+    const uint32_t tap_stride16 = (static_cast<uint32_t>(p.TW) * 128u) >> 4;
+    const uint32_t idesc = p.idesc;
+    constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+    constexpr uint32_t kDescLoFlags = 1u << 16;
+    int it = 0;
+    for (int tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
+      const TileCoord tc = decode_tile<1>(p, 0, tile);
+      const int st = it & 1;
+      wait_bar(&accEmpty[st], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this TMEM stage (free on first use)
+      ptx::tc_fence_after();
+      const uint32_t d = tmem_base + static_cast<uint32_t>(st) * 256u;
+      uint32_t accumulate = 0;
+      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
+        wait_bar(&fullA[slotA], phaseA);
+        const int ch_left = p.Cin - cb * 64;
+        const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
+        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+        for (int khs = 0; khs < p.KHs; ++khs) {
+          wait_bar(&fullB[slotB], phaseB);
+          ptx::tc_fence_after();
+          const uint32_t w_lo = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+          const uint32_t x_lo = a_lo0 + static_cast<uint32_t>(khs) * tap_stride16;
+          if (ptx::elect_one()) {
+            for (int k = 0; k < ksteps; ++k)
+              ptx::umma_f16_lohi(d, w_lo + 2 * k, x_lo + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+            ptx::umma_commit(&emptyB[slotB]);
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (++slotB == p.NB) {
+            slotB = 0;
+            phaseB ^= 1;
+          }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(&emptyA[slotA]);
+        __syncwarp();
+        if (++slotA == p.NA) {
+          slotA = 0;
+          phaseA ^= 1;
+        }
+      });
+      if (ptx::elect_one()) ptx::umma_commit(&accFull[st]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------- epilogue warps
+    const int ew = warp - 4;           // 0..7
+    const int q = warp & 3;            // TMEM lane quarter (warp id mod 4)
+    const int grp = ew >> 2;           // which half of the 8 items of a tile
+    uint8_t* stage = sStage + static_cast<size_t>(ew) * 4096;
+    uint32_t res_phase = 0;
+    int nbuf = 0;
+    const int c_me = q * 32 + lane;    // output channel owned by this thread (n0 == 0: Cout == 128)
+    const float bias_c = p.bias ? __ldg(p.bias + c_me) : 0.f;
+    float gs = 0.f, gq = 0.f;
+    int cur_b = -1;
+    auto flush_stats = [&](int b) {
+      if (!p.gn_stats || b < 0) return;
+      float ts = gs, tq = gq;
+      for (int o = 1; o < p.gn_cpg && o < 32; o <<= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        tq += __shfl_xor_sync(0xffffffffu, tq, o);
+      }
+      const int lanes_per_group = min(p.gn_cpg, 32);
+      if ((lane % lanes_per_group) == 0) {
+        unsigned long long* o64 = reinterpret_cast<unsigned long long*>(p.gn_stats) + (static_cast<size_t>(b) * p.gn_groups + c_me / p.gn_cpg) * 2;
+        atomicAdd(o64, gn_fix(ts, kGnSumScale));
+        atomicAdd(o64 + 1, gn_fix(tq, kGnSqScale));
+      }
+      gs = gq = 0.f;
+    };
+    int it = 0;
+    for (int tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
+      const TileCoord tc = decode_tile<1>(p, 0, tile);
+      const int st = it & 1;
+      if (tc.b != cur_b) {
+        flush_stats(cur_b);
+        cur_b = tc.b;
+      }
+      wait_bar(&accFull[st], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const int rows_valid = min(p.TH, max(0, p.H_out - tc.h0));  // rows of this tile inside the image
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = grp * 4 + jj;                 // 32-position chunk of the 256-position tile
+        const int f0 = j * 32;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(st * 256 + f0), v);
+        ptx::tmem_ld_wait();
+        if (jj == 3) {
+          // last TMEM read of this tile by this warp: hand the stage back to the MMA warp before the stores
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(&accEmpty[st]);
+        }
+        if (f0 / p.TW >= rows_valid) continue;       // chunk entirely below the image (warp-uniform)
+        const int h = tc.h0 + f0 / p.TW, w = tc.w0 + f0 % p.TW;
+        const int hi = tc.h0 + (f0 + lane) / p.TW, wi = tc.w0 + (f0 + lane) % p.TW;
+        const unsigned valid = __ballot_sync(0xffffffffu, (hi < p.H_out) && (wi < p.W_out));
+        uint8_t* tilebuf = stage + (nbuf & 1) * 2048;
+        const uint32_t tile_u32 = ptx::smem_u32(tilebuf);
+        if (lane == 0) ptx::bulk_wait_read<1>();
+        __syncwarp();
+        if (p.residual) {
+          if (lane == 0) {
+            ptx::mbar_expect_tx(&resBar[ew], 2048);
+            ptx::tma_load_5d(tilebuf, &tmR, &resBar[ew], q * 32, w, h, tc.t, tc.b);
+          }
+          wait_bar(&resBar[ew], res_phase);
+          res_phase ^= 1;
+        }
+        const uint32_t my = tile_u32 + static_cast<uint32_t>(lane) * 2u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = fmaf(__uint_as_float(v[i]), p.alpha, bias_c);
+          if (p.residual) {
+            uint16_t r16;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r16) : "r"(my + i * 64u));
+            a += E::to_f(*reinterpret_cast<const typename E::T*>(&r16));
+          }
+          const typename E::T o = E::from_f(a);
+          if (p.gn_stats && ((valid >> i) & 1u)) {
+            const float of = E::to_f(o);
+            gs += of;
+            gq = fmaf(of, of, gq);
+          }
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(my + i * 64u), "h"(*reinterpret_cast<const uint16_t*>(&o)) : "memory");
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_5d(&tmY, tilebuf, q * 32, w, h, tc.t, tc.b);
+          ptx::bulk_commit();
+        }
+        ++nbuf;
+      }
+    }
+    flush_stats(cur_b);
+    if (lane == 0) ptx::bulk_wait<0>();
+    __syncwarp();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------- host side
 static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
                        const cuuint32_t* box, const cuuint32_t* estr,
@@ -808,6 +1066,15 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     }();
     if (nacc_env > 0 && nacc_env < p.NACC) p.NACC = nacc_env;
   }
+  // persistent double-buffered variant for the Cout == 128 layers: tiles of 256 positions (two 128-row sub-tiles)
+  static const int persist_env = [] {
+    const char* e = getenv("CVVAE_CONV_PERSIST");
+    return e ? atoi(e) : 1;
+  }();
+  const bool flat_shape = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1);
+  const bool persist_want = persist_env && !flat_shape && p.Cout == 128 && N_cta == 128 && p.up_time == 1 && p.vec_ok &&
+                            !(d->flags & (CVVAE_CONV_BIAS_ALONG_M | CVVAE_CONV_OUT_F32)) && y.C % 32 == 0;
+  if (persist_want) p.NACC = 2;
   p.flat = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1) ? 1 : 0;
   p.cblocks = (p.Cin + 63) / 64;
   if (p.flat) {
@@ -857,7 +1124,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128 * CG, N_cta);
 
   // ---- shared memory budget: 227 KB - alignment slack - barriers
-  const size_t budget = 232448 - 1024 - 1536;
+  const size_t budget = 232448 - 1024 - 1536 - (persist_want ? 32768 : 0);  // persistent kernel: own staging area
   int NB = 4;
   while (NB > 2 && static_cast<size_t>(NB) * p.b_bytes + 2ull * p.slab_bytes > budget) --NB;
   size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;
@@ -868,7 +1135,8 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_bytes <= budget) ++NB;
   p.NA = NA;
   p.NB = NB;
-  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 1536;
+  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 1536 +
+                      (persist_want ? 32768 : 0);
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
@@ -927,6 +1195,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
         if (!encode_map(&tmY, y.ptr, 5, dims, strides, box2, estr, CU_TENSOR_MAP_SWIZZLE_NONE)) return CVVAE_E_CUDA;
         if (d->residual && !encode_map(&tmR, d->residual, 5, dims, strides, box2, estr, CU_TENSOR_MAP_SWIZZLE_NONE)) return CVVAE_E_CUDA;
         p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128, 256);
+        p.persist = (persist_want && p.NACC == 2) ? 1 : 0;
       }
     }
   }
@@ -955,7 +1224,16 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
       CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
       attr_set = true;
     }
-    if (CG == 2) {
+    if (p.persist) {
+      static bool pattr = false;
+      if (!pattr) {
+        CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_psw_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        pattr = true;
+      }
+      p.n_tiles = static_cast<int>(grid);
+      const int ctas = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+      conv_tc_psw_kernel<DT><<<ctas, kPersistThreads, smem, stream>>>(tmA, tmB, tmY, tmR, p);
+    } else if (CG == 2) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(static_cast<unsigned>(grid));
       cfg.blockDim = dim3(kThreads);

@@ -55,6 +55,9 @@ def main():
         ops.lib.cvvae_conv_tc_set_trace(None, 0)
         t = buf.cpu().numpy().astype(np.uint64)
         t = t[t[:, 0] > 0]
+        if len(t) == 0:  # persistent kernel: no per-CTA stamps
+            print(json.dumps({"layer": name, "kernel_ms": round(s_ev.elapsed_time(e_ev), 3), "ctas_traced": 0}), flush=True)
+            continue
         smid = (t[:, 7] >> np.uint64(48)).astype(np.int64)
         t7 = (t[:, 7] & np.uint64(0xFFFFFFFFFFFF)).astype(np.int64)
         tt = t.astype(np.int64)
