@@ -92,3 +92,24 @@ def test_forward_and_4d_paths():
     gold = np.load(os.path.join(GOLD, "sd21_w32_image.npz"))
     d = (rec4.float().cpu() - torch.from_numpy(gold["recon_4d"])).abs()
     assert d.max().item() < 5e-2 and d.mean().item() < 5e-3
+
+
+@pytest.mark.parametrize("variant,shape", [("sd21", (1, 3, 5, 40, 56)), ("sd21", (2, 3, 9, 24, 72)), ("sd21", (1, 3, 1, 16, 16)),
+                                           ("sd21", (1, 3, 13, 100, 44)), ("sd3", (1, 3, 5, 40, 56)), ("sd3", (2, 3, 1, 24, 24))])
+def test_ragged_shapes_vs_oracle(variant, shape):
+    """Edge shapes the reference accepts (single frame, sizes that are not multiples of the tile / of 16, batch > 1,
+    odd down-sampled extents) against the fp32 oracle computed on the spot (width-32 models, no tiling)."""
+    wrap = dict(tile_spatial_size=None, en_de_n_frames_a_time=None)
+    case = dict(variant=variant, ch=32, wrap=wrap)
+    m, cfg, sd = _build(case, torch.float16)
+    x = O.synthetic_video(shape, 11)
+    with torch.no_grad():
+        opost = O.encode(x, sd, cfg)
+        orec = O.decode(opost.mode(), sd, cfg)
+    post = m.encode(x.half().cuda()).latent_dist
+    rec = m.decode(post.mode()).sample
+    assert post.parameters.shape == opost.parameters.shape and rec.shape == orec.shape
+    em = (post.parameters.float().cpu() - opost.parameters).abs()
+    er = (rec.float().cpu() - orec).abs()
+    assert em.max().item() < 3e-2 and em.mean().item() < 3e-3, (em.max().item(), em.mean().item())
+    assert er.max().item() < 8e-2 and er.mean().item() < 8e-3, (er.max().item(), er.mean().item())
