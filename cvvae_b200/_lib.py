@@ -44,6 +44,7 @@ _SIGNATURES = {
     "cvvae_conv3d_tc": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "cvvae_conv3d_direct": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "cvvae_conv3d_is_tc": (C.c_int, [C.POINTER(ConvDesc)]),
+    "cvvae_conv3d_stacked": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "cvvae_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "cvvae_groupnorm_stats": (C.c_int, [_P5, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "cvvae_groupnorm_apply": (C.c_int, [_P5, _P5, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,

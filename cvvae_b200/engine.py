@@ -92,6 +92,12 @@ def prepack_params(state_dict: Dict[str, torch.Tensor], ops, dtype: torch.dtype)
                         packed[k[: -len("weight")] + f"phase{ph}{pw}.weight"] = ops.pack_weight(wf)
                 continue
             packed[k] = ops.pack_weight(v)
+            if k == "decoder.conv_out.weight" and v.dim() == 5 and v.shape[0] <= 4 and tuple(v.shape[3:]) == (3, 3):
+                # tap-stacked form for the tiny-Cout kernel: [KT][80][Cin], row (kh*3+kw)*8 + c
+                co, ci, kt = v.shape[0], v.shape[1], v.shape[2]
+                stk = torch.zeros((kt, 80, ci), dtype=dtype, device=v.device)
+                stk[:, :72].view(kt, 9, 8, ci)[:, :, :co] = v.permute(2, 3, 4, 0, 1).reshape(kt, 9, co, ci)
+                packed[k + ".stk"] = stk
         else:
             packed[k] = v.detach().to(torch.float32).contiguous()
     return packed
@@ -383,7 +389,19 @@ class Engine:
         h = self.gn(h, D + ("conv_norm_out" if self.sd3 else "norm_out"), framed=self.sd3)
         B, T, H, W, _ = h.t.shape
         out = torch.empty((B, cfg.out_ch, T, H, W), dtype=z.dtype, device=z.device)
-        self.conv3(h, D + "conv_out", causal, out=out.permute(0, 2, 3, 4, 1))
+        stk = self.p.get(D + "conv_out.weight.stk")
+        if stk is not None and hasattr(self.ops, "conv_stacked"):
+            # 128 -> 3 at full resolution: tap-stacked kernel (N = 16 MMAs are bound by A-operand reads)
+            if self.sd3:
+                tl, pad_t = (2 if causal else 1), PAD_REPLICATE
+                x_in, off = h.pad, (-tl, 0, 0)        # framed input: replicate border already in place
+            else:
+                tl, pad_t = ((2, PAD_REPLICATE) if causal else (1, PAD_ZERO))
+                x_in, off = h.t, (-tl, -1, -1)
+            self.ops.conv_stacked(x_in, stk, self.p.get(D + "conv_out.bias"), kt=stk.shape[0], cout=cfg.out_ch, offset=off,
+                                  pad_t=pad_t, pad_hw=PAD_ZERO, out=out.permute(0, 2, 3, 4, 1))
+        else:
+            self.conv3(h, D + "conv_out", causal, out=out.permute(0, 2, 3, 4, 1))
         return out
 
     def upsample(self, a: Act, name: str, up_time: int, causal: bool) -> Act:

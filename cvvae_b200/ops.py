@@ -151,6 +151,39 @@ class CudaOps:
         self.profile["events"][path].append((s_ev, e_ev))
         return out
 
+    def conv_stacked(self, x: torch.Tensor, w_stk: torch.Tensor, bias: Optional[torch.Tensor], *, kt: int, cout: int,
+                     offset=(0, -1, -1), pad_t=L.PAD_ZERO, pad_hw=L.PAD_ZERO, out: torch.Tensor = None) -> torch.Tensor:
+        """(KT x) 3 x 3 stride-1 convolution with Cout <= 4 through the tap-stacked kernel; w_stk is [KT, 80, Cin]."""
+        assert w_stk.shape[0] == kt and w_stk.shape[1] == 80 and w_stk.is_contiguous()
+        d = L.ConvDesc()
+        d.x = _t5(x)
+        d.y = _t5(out)
+        d.w = w_stk.data_ptr()
+        d.bias = _ptr(bias)
+        d.Cout = cout
+        d.KT, d.KH, d.KW = kt, 3, 3
+        d.st = d.sh = d.sw = 1
+        d.off_t, d.off_h, d.off_w = offset
+        d.pad_t, d.pad_hw = pad_t, pad_hw
+        d.up_time = 1
+        d.dtype = dtype_code(x.dtype)
+        d.alpha = 1.0
+        if self.profile is not None:
+            B, T, H, W, Ci = x.shape
+            fl = 2 * B * out.shape[1] * out.shape[2] * out.shape[3] * cout * Ci * kt * 9
+            self.profile["flops"]["conv_tc"] += fl
+            self.profile["ref_flops"]["conv_tc"] += fl
+            self.profile["bytes"]["conv_tc"] += x.numel() * x.element_size() + out.numel() * out.element_size()
+            self.profile["launches"]["conv_tc"] += 1
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_ev.record()
+            L.check(self.lib.cvvae_conv3d_stacked(C.byref(d), _stream(x)), "cvvae_conv3d_stacked")
+            e_ev.record()
+            self.profile["events"]["conv_tc"].append((s_ev, e_ev))
+        else:
+            L.check(self.lib.cvvae_conv3d_stacked(C.byref(d), _stream(x)), "cvvae_conv3d_stacked")
+        return out
+
     # ------------------------------------------------------------------ normalisation
     def new_stats(self, B: int, groups: int, device) -> torch.Tensor:
         """Zeroed int64 fixed-point [B, groups, 2] accumulator (sum * 2^20, sum^2 * 2^18) for conv-epilogue statistics."""

@@ -99,6 +99,13 @@ int cvvae_conv3d_direct(const cvvae_conv_desc* d, void* stream); /* CUDA-core pa
 /* 1 if cvvae_conv3d() would take the tensor-core path for this descriptor, else 0. */
 int cvvae_conv3d_is_tc(const cvvae_conv_desc* d);
 
+/* Tap-stacked kernel for stride-1 (KT x) 3 x 3 convolutions with Cout <= 4 (Decoder.conv_out, 128 -> 3 at full
+ * resolution; reference models/vae_models.py:942-944,999): the nine (kh,kw) taps are stacked along the MMA's N
+ * dimension and the spatial shifts applied to the per-position partial sums afterwards.  Same descriptor as
+ * cvvae_conv3d, except that `w` holds the STACKED weights [KT][80][Cin] (row (kh*3+kw)*8 + c, all other rows zero);
+ * no residual / statistics / fp32 output.  pad_hw == REPLICATE needs a framed input (off_h = off_w = 0). */
+int cvvae_conv3d_stacked(const cvvae_conv_desc* d, void* stream);
+
 /* [Cout][Cin][KT][KH][KW] (PyTorch layout, contiguous, activation dtype) -> [KT*KH*KW][Cout][Cin]. */
 int cvvae_pack_conv_weight(const void* w_oikkk, void* w_packed, int32_t Cout, int32_t Cin, int32_t taps,
                            int32_t dtype, void* stream);

@@ -106,6 +106,12 @@ class FakeOps:
             gn_stats[:, :, 1] += torch.round((g * g).sum(dim=(1, 3)) * GN_SQ_SCALE).to(torch.int64)
         return out
 
+    def conv_stacked(self, x, w_stk, bias, *, kt, cout, offset=(0, -1, -1), pad_t=PAD_ZERO, pad_hw=PAD_ZERO, out=None):
+        # [KT][80][Cin] (row (kh*3+kw)*8 + c) -> packed [KT*9][Cout][Cin]
+        ci = w_stk.shape[2]
+        w = w_stk[:, :72].reshape(kt, 9, 8, ci)[:, :, :cout].reshape(kt * 9, cout, ci)
+        return self.conv(x, w, bias, kernel=(kt, 3, 3), offset=offset, pad_t=pad_t, pad_hw=pad_hw, out=out)
+
     def new_stats(self, B, groups, device):
         return torch.zeros((B, groups, 2), dtype=torch.int64, device=device)
 

@@ -302,3 +302,22 @@ def test_conv_pairs_forced_everywhere():
                         "test_conv_tc_matches_spec or test_conv_fused_groupnorm_stats"], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("shape,cout,kt,off_t,pad_t", [((1, 3, 40, 50, 128), 3, 3, -1, PAD_ZERO), ((2, 5, 33, 61, 128), 3, 3, -2, PAD_REPLICATE),
+                                                       ((1, 2, 16, 16, 64), 4, 3, -1, PAD_REPLICATE), ((1, 1, 70, 30, 128), 3, 1, 0, PAD_ZERO)])
+def test_conv_stacked_matches_spec(shape, cout, kt, off_t, pad_t):
+    """Tap-stacked tiny-Cout kernel (decoder conv_out) vs the conv spec, NCDHW scatter output."""
+    ops, fake = _ops(), FakeOps()
+    B, T, H, W, Ci = shape
+    x = _rand(shape, torch.float16, 50)
+    w = _rand((kt * 9, cout, Ci), torch.float16, 51, scale=(kt * 9 * Ci) ** -0.5 * 2)
+    stk = torch.zeros((kt, 80, Ci), dtype=torch.float16, device=DEV)
+    stk[:, :72].view(kt, 9, 8, Ci)[:, :, :cout] = w.view(kt, 9, cout, Ci)
+    bias = _rand((cout,), torch.float32, 52, 0.3)
+    got = torch.zeros((B, cout, T, H, W), dtype=torch.float16, device=DEV)
+    want = torch.zeros((B, T, H, W, cout), dtype=torch.float32, device=DEV)
+    ops.conv_stacked(x, stk, bias, kt=kt, cout=cout, offset=(off_t, -1, -1), pad_t=pad_t, out=got.permute(0, 2, 3, 4, 1))
+    fake.conv(x, w, bias, kernel=(kt, 3, 3), offset=(off_t, -1, -1), pad_t=pad_t, out=want)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(got.permute(0, 2, 3, 4, 1).float(), want, **_tol(torch.float16))
