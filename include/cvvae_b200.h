@@ -157,6 +157,13 @@ int cvvae_copy5(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, v
 int cvvae_blend(const cvvae_tensor5* a, const cvvae_tensor5* b, int32_t overlap, int32_t axis, int32_t dtype,
                 void* stream);
 
+/* Pixel pre/post-processing of the inference script, one pass each, bit-exact with the reference expressions:
+ *   u8_to_f16:  uint8 frames [T,H,W,3] -> 16-bit [3,T,H,W] = frame.half() / 127.5 - 1.0   (cvvae_inference_video.py:30-38)
+ *   f16_to_u8:  16-bit [3,T,H,W] -> uint8 [T,H,W,3] = ((clamp(x,-1,1) + 1.0) * 127.5).to(uint8)   (:47-50)
+ * Both tensors are contiguous device buffers. */
+int cvvae_video_u8_to_f16(const uint8_t* thwc, void* out_cthw, int32_t T, int32_t H, int32_t W, int32_t dtype, void* stream);
+int cvvae_video_f16_to_u8(const void* in_cthw, uint8_t* thwc, int32_t T, int32_t H, int32_t W, int32_t dtype, void* stream);
+
 /* Diagnostics */
 /* Per-CTA phase timestamps of the next conv_tc launches: device buffer of n_ctas x 8 uint64 (globaltimer ns:
  * entry, setup done, first A landed, first B landed, all MMAs issued, accumulators ready, epilogue done,

@@ -321,3 +321,20 @@ def test_conv_stacked_matches_spec(shape, cout, kt, off_t, pad_t):
     fake.conv(x, w, bias, kernel=(kt, 3, 3), offset=(off_t, -1, -1), pad_t=pad_t, out=want)
     torch.cuda.synchronize()
     torch.testing.assert_close(got.permute(0, 2, 3, 4, 1).float(), want, **_tol(torch.float16))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_video_pre_post_processing_bit_exact(dtype):
+    """Fused uint8<->16-bit pixel conversion equals the reference script's expressions bit for bit."""
+    from cvvae_b200.video_io import frames_to_input, output_to_frames
+    g = torch.Generator().manual_seed(60)
+    frames = torch.randint(0, 256, (5, 36, 52, 3), generator=g, dtype=torch.uint8).to(DEV)
+    frames[0, 0, 0] = torch.tensor([0, 255, 128], dtype=torch.uint8)
+    got = frames_to_input(frames, dtype)
+    # cvvae_inference_video.py:30-34 runs this on the CPU tensor (true division), before .cuda()
+    want = frames.cpu().permute(3, 0, 1, 2).unsqueeze(0).to(dtype) / 127.5 - 1.0
+    assert got.dtype == dtype and torch.equal(got.cpu(), want)
+    x = (_rand((1, 3, 5, 36, 52), torch.float32, 61, 1.3)).to(dtype)             # includes values outside [-1, 1]
+    got8 = output_to_frames(x)
+    want8 = ((torch.clamp(x, -1.0, 1.0) + 1.0) * 127.5).to(torch.uint8).squeeze(0).permute(1, 2, 3, 0)  # :47-50
+    assert torch.equal(got8, want8)
