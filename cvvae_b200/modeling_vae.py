@@ -147,6 +147,10 @@ class _CVVAEBase(nn.Module):
         self.reshape_z_dim_to_4 = reshape_z_dim_to_4
         self.reshape_x_dim_to_4 = reshape_x_dim_to_4
         self._engine_cache = None
+        self._graphs_enabled = False
+        self._graph_cache = {}
+        self._graph_pool = None
+        self._graph_max = 8
         self.requires_grad_(False)
         self.eval()
 
@@ -194,6 +198,7 @@ class _CVVAEBase(nn.Module):
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         self._engine_cache = None
+        self._graph_cache = {}
         # the sd3 reference registers the same down-sampler conv under two names in some diffusers versions;
         # tolerate the alias when present
         sd = {k: v for k, v in state_dict.items() if ".Conv2d_0." not in k}
@@ -201,6 +206,7 @@ class _CVVAEBase(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._engine_cache = None
+        self._graph_cache = {}
         return super()._apply(fn, *a, **k)
 
     # ---- engine ---------------------------------------------------------------
@@ -222,10 +228,52 @@ class _CVVAEBase(nn.Module):
             self._engine_cache = (key, Engine(self.net, packed, ops, p0.dtype))
         return self._engine_cache[1]
 
+    def enable_cuda_graphs(self, enabled: bool = True, max_cached: int = 8):
+        """Replay each network call (one encoder / decoder pass over a tile batch) as a captured CUDA graph.
+
+        The chunk/tile work list of one clip launches ~600 kernels per tile; at small tiles (image path, 256^2 clips,
+        the 72^2 mid-block) the host cannot issue them as fast as the GPU retires them.  One graph is captured per
+        (direction, input shape) on first use - `max_cached` of them are kept, sharing one memory pool - and later
+        calls copy the input into the graph's static buffer and replay.  Results are identical to the eager path
+        (same kernels, same order).  
+        """
+        self._graphs_enabled = bool(enabled)
+        self._graph_max = int(max_cached)
+        if not enabled:
+            self._graph_cache = {}
+        return self
+
+    def _run_net_eager(self, eng: Engine, which: str, x: torch.Tensor) -> torch.Tensor:
+        return eng.encode(x) if which == "encode" else eng.decode(x)
+
     def _run_net(self, which: str, x: torch.Tensor) -> torch.Tensor:
         self._check_input(x)
         eng = self._engine()
-        return eng.encode(x) if which == "encode" else eng.decode(x)
+        if (not self._graphs_enabled or self._ops_factory is not None or getattr(eng.ops, "profile", None) is not None
+                or torch.cuda.is_current_stream_capturing()):
+            return self._run_net_eager(eng, which, x)
+        key = (which, tuple(x.shape))
+        entry = self._graph_cache.get(key)
+        if entry is None:
+            static_in = x.detach().clone(memory_format=torch.contiguous_format)
+            cur = torch.cuda.current_stream(x.device)
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):               # one eager pass first: module loading, func attributes, allocator warm-up
+                self._run_net_eager(eng, which, static_in)
+            cur.wait_stream(side)
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                static_out = self._run_net_eager(eng, which, static_in)
+            while len(self._graph_cache) >= max(1, self._graph_max):
+                self._graph_cache.pop(next(iter(self._graph_cache)))
+            entry = self._graph_cache[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
 
     def _check_input(self, x):
         if x.dtype != self.dtype:

@@ -113,3 +113,24 @@ def test_ragged_shapes_vs_oracle(variant, shape):
     er = (rec.float().cpu() - orec).abs()
     assert em.max().item() < 3e-2 and em.mean().item() < 3e-3, (em.max().item(), em.mean().item())
     assert er.max().item() < 8e-2 and er.mean().item() < 8e-3, (er.max().item(), er.mean().item())
+
+
+@pytest.mark.parametrize("name", ["sd21_w32_tiled", "sd3_w32_plain"])
+def test_cuda_graph_replay_is_bit_identical(name):
+    """enable_cuda_graphs(): captured replay == eager launches, also for a second input through the same graphs."""
+    case = CASES[name]
+    m, cfg, sd = _build(case, torch.float16)
+    xs = [O.synthetic_video(case["shape"], MANIFEST["input_seed"] + i).half().cuda() for i in range(2)]
+    eager = []
+    for x in xs:
+        post = m.encode(x).latent_dist
+        eager.append((post.parameters.clone(), m.decode(post.mode()).sample.clone()))
+    m.enable_cuda_graphs(True)
+    for rep in range(2):                      # first pass captures, second replays
+        for x, (mom, rec) in zip(xs, eager):
+            post = m.encode(x).latent_dist
+            got = m.decode(post.mode()).sample
+            assert torch.equal(post.parameters, mom) and torch.equal(got, rec)
+    assert len(m._graph_cache) >= 2
+    m.enable_cuda_graphs(False)
+    assert not m._graph_cache
