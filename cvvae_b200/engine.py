@@ -139,11 +139,22 @@ class Engine:
         want_stats: also produce the consumer GroupNorm's (sum, sum^2) per (sample, group) in the epilogue
         (`stats` continues an accumulator across the launches that fill one tensor)."""
         x = a.t
-        w = self.p[weight_key or (name + ".weight")]
+        wkey = weight_key or (name + ".weight")
+        w = self.p[wkey]
         b = self.p.get(name + ".bias")
         B, T, H, W, _ = x.shape
         (tl, th), (hl, hh), (wl, wh) = pads
         kt, kh, kw = kernel
+        if T == 1 and kt > 1 and _out_len(1, kt, stride[0], tl, th) == 1:
+            # single-frame input (image path, SURVEY 8f row 4): every time tap reads frame 0 (replicate padding) or
+            # nothing (zero padding), so the conv is a per-frame one with pre-summed / selected time taps; of an
+            # `up_time` conv only the channel half that lands on the kept frame is computed
+            w, b = self._single_frame_weights(wkey, name, w, b, kt, kh * kw, tl, pad_t, up_time)
+            if ref_taps is None:
+                ref_taps = kt * kh * kw
+            kernel, stride, pads = (1, kh, kw), (1, stride[1], stride[2]), ((0, 0), (hl, hh), (wl, wh))
+            tl = th = 0
+            kt, up_time, pad_t = 1, 1, PAD_ZERO
         Co = w.shape[1]
         To = _out_len(T, kt, stride[0], tl, th)
         Ho = _out_len(H, kh, stride[1], hl, hh)
@@ -205,6 +216,27 @@ class Engine:
             self.ops.conv(x, w, b, kernel=kernel, stride=stride, offset=off, pad_t=pad_t, pad_hw=pad_hw,
                           up_time=up_time, residual=residual, out=out, ref_taps=ref_taps, **skw)
         return Act(out, stats=stats)
+
+    def _single_frame_weights(self, wkey, name, w, b, kt, khw, tl, pad_t, up_time):
+        """[kt*khw, Co, Ci] -> [khw, Co', Ci] for a one-frame input (cached in the parameter table)."""
+        key = f"{wkey}.t1.{tl}.{pad_t}.{up_time}"
+        if key not in self.p:
+            w4 = w.view(kt, khw, w.shape[1], w.shape[2])
+            if pad_t == PAD_REPLICATE:
+                wf = w4.float().sum(0).to(w.dtype)      # one rounding of the fp32 sum
+            elif 0 <= tl < kt:
+                wf = w4[tl]
+            else:
+                wf = torch.zeros_like(w4[0])
+            bf = b
+            if up_time == 2:                            # "b (n c) t h w -> b c (t n) h w" then drop frame 0: keep n = 1
+                half = w.shape[1] // 2
+                wf = wf[:, half:]
+                bf = b[half:].contiguous() if b is not None else None
+            self.p[key] = wf.contiguous()
+            if bf is not None:
+                self.p[key + ".bias"] = bf
+        return self.p[key], self.p.get(key + ".bias")
 
     def conv3(self, a: Act, name: str, causal: bool, **kw) -> Act:
         """3x3x3, stride 1, 'same': CausalConv3d / nn.Conv3d(padding=1) / Conv3d(replicate)."""

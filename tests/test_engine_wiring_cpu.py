@@ -74,3 +74,22 @@ def test_surface_matches_reference_contract(tmp_path):
     out = m(x).sample
     assert torch.equal(out, rec) and rec.shape == x.shape
     assert m.encoder(x).shape == (1, 8, 2, 2, 2)
+
+
+@pytest.mark.parametrize("variant", ["sd21", "sd3"])
+def test_single_frame_time_tap_folding(variant):
+    """T = 1 (image path): the engine folds the time taps of every 3x3x3 conv and computes only the kept half of the
+    up_time convs; the result must equal the oracle's literal execution (pad, conv, interleave, drop)."""
+    case = dict(variant=variant, ch=32, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None))
+    m, cfg = build_model(case)
+    sd = O.make_state_dict(cfg, MANIFEST["weight_seed"])
+    x = O.synthetic_video((2, 3, 1, 40, 24), 5)
+    want_post = O.encode(x, sd, cfg)
+    want_rec = O.decode(want_post.mode(), sd, cfg)
+    post = m.encode(x).latent_dist
+    rec = m.decode(post.mode()).sample
+    assert rec.shape == want_rec.shape == (2, 3, 1, 40, 24)
+    np.testing.assert_allclose(post.parameters.numpy(), want_post.parameters.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(rec.numpy(), want_rec.numpy(), rtol=1e-4, atol=5e-5)
+    folded = [k for k in m._engine().p if ".t1." in k and not k.endswith(".bias")]
+    assert folded and all(m._engine().p[k].shape[0] in (4, 9) for k in folded)     # 2x2 phases / 3x3: no time taps left

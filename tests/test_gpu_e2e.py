@@ -95,7 +95,8 @@ def test_forward_and_4d_paths():
 
 
 @pytest.mark.parametrize("variant,shape", [("sd21", (1, 3, 5, 40, 56)), ("sd21", (2, 3, 9, 24, 72)), ("sd21", (1, 3, 1, 16, 16)),
-                                           ("sd21", (1, 3, 13, 100, 44)), ("sd3", (1, 3, 5, 40, 56)), ("sd3", (2, 3, 1, 24, 24))])
+                                           ("sd21", (1, 3, 13, 100, 44)), ("sd3", (1, 3, 5, 40, 56)), ("sd3", (2, 3, 1, 24, 24)),
+                                           ("sd21", (1, 3, 1, 64, 96))])
 def test_ragged_shapes_vs_oracle(variant, shape):
     """Edge shapes the reference accepts (single frame, sizes that are not multiples of the tile / of 16, batch > 1,
     odd down-sampled extents) against the fp32 oracle computed on the spot (width-32 models, no tiling)."""

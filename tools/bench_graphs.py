@@ -50,6 +50,18 @@ def main():
         m.enable_cuda_graphs(False)
         out[name] = row
         print(name, json.dumps(row), flush=True)
+    # SD-pipeline call: 4-D latents, decode(z / scaling_factor, num_frames=1)  (pipeline_stable_diffusion.py:1046)
+    for name, shp in {"sd_pipeline_decode_1x64x64_latent": (1, 4, 64, 64), "sd_pipeline_decode_4x64x64_latent": (4, 4, 64, 64),
+                      "sd_pipeline_decode_1x128x128_latent": (1, 4, 128, 128)}.items():
+        z = (torch.randn(shp, generator=torch.Generator().manual_seed(3)) * 0.5).half().cuda()
+        row = {}
+        for mode in ("eager", "graphs"):
+            m.enable_cuda_graphs(mode == "graphs")
+            dev, wall = timeit(lambda: m.decode(z, num_frames=1).sample, n=10)
+            row[mode] = {"device_ms": round(dev, 3), "wall_ms": round(wall, 3), "images_per_s": round(shp[0] / dev * 1e3, 1)}
+        m.enable_cuda_graphs(False)
+        out[name] = row
+        print(name, json.dumps(row), flush=True)
     with open("gpurun_out/bench_graphs.json", "w") as f:
         json.dump(out, f, indent=1)
 
