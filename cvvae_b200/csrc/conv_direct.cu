@@ -148,7 +148,7 @@ __global__ void pack_weight_kernel(const typename Elem<DT>::T* __restrict__ src,
 
 bool conv_tc_eligible(const cvvae_conv_desc* d, const char** why);
 int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream);
-int gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats, int32_t dtype,
+int gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, int64_t* stats, int32_t dtype,
                  cudaStream_t stream, bool zero_first);
 
 }  // namespace cvvae

@@ -44,7 +44,7 @@ struct ConvTcParams {
   void* y;
   long long ys_b, ys_t, ys_h, ys_w, ys_c;
   int yC, yT, vec_ok, bias_vec;
-  double* gn_stats;  // fused GroupNorm statistics of y (TMA epilogue only)
+  int64_t* gn_stats;  // fused GroupNorm statistics of y (TMA epilogue only)
   int gn_groups, gn_cpg;
   int persist;  // persistent swap kernel: 256-position tiles, two TMEM stages, epilogue overlapped with the next tile
   int n_tiles;  // tiles of the whole launch (persistent kernel)

@@ -128,7 +128,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnView v, unsigned 
   }
 }
 
-template <int DT>
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int DT, int U, int HINT>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const long long* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int silu) {
@@ -186,8 +196,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const lon
     }
     return make_uint4(ow[0], ow[1], ow[2], ow[3]);
   };
-  constexpr int U = 4;  // independent 128-bit loads in flight per thread
-  long long p = p0 + pl;
+  long long p = p0 + pl;   // U independent 128-bit loads in flight per thread
   for (; p + static_cast<long long>(U - 1) * lanes < p1; p += static_cast<long long>(U) * lanes) {
     uint4 u[U];
     long long yo[U];
@@ -196,10 +205,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnView v, const lon
       const long long pp = p + static_cast<long long>(i) * lanes;
       const long long xo = gn_offset(pp, ut, v.per_frame, v.H, v.W, v.xs_t, v.xs_h, v.xs_w, v.x_dense, v.C);
       yo[i] = gn_offset(pp, ut, v.per_frame, v.H, v.W, v.ys_t, v.ys_h, v.ys_w, v.y_dense, v.C);
-      u[i] = __ldg(reinterpret_cast<const uint4*>(xb + xo + vec * 8));
+      u[i] = HINT ? ld_stream(xb + xo + vec * 8) : __ldg(reinterpret_cast<const uint4*>(xb + xo + vec * 8));
     }
 #pragma unroll
-    for (int i = 0; i < U; ++i) *reinterpret_cast<uint4*>(yb + yo[i] + vec * 8) = transform(u[i]);
+    for (int i = 0; i < U; ++i) {
+      if (HINT) st_stream(yb + yo[i] + vec * 8, transform(u[i]));
+      else *reinterpret_cast<uint4*>(yb + yo[i] + vec * 8) = transform(u[i]);
+    }
   }
   for (; p < p1; p += lanes) {
     const long long xo = gn_offset(p, ut, v.per_frame, v.H, v.W, v.xs_t, v.xs_h, v.xs_w, v.x_dense, v.C);
@@ -324,17 +336,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const GnView v, long lon
 using namespace cvvae;
 
 namespace cvvae {
-int gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats, int32_t dtype,
+int gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, int64_t* stats, int32_t dtype,
                  cudaStream_t stream, bool zero_first);
 }
 
-extern "C" int cvvae_groupnorm_stats(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats,
+extern "C" int cvvae_groupnorm_stats(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, int64_t* stats,
                                      int32_t dtype, void* stream_) {
   CVVAE_CHECK_ARG(tensor_ok(x) && stats, "cvvae_groupnorm_stats: null argument");
   return cvvae::gn_stats_run(x, groups, per_frame, stats, dtype, static_cast<cudaStream_t>(stream_), true);
 }
 
-int cvvae::gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats, int32_t dtype,
+int cvvae::gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, int64_t* stats, int32_t dtype,
                         cudaStream_t stream, bool zero_first) {
   GnView v{};
   int rc = fill_view(v, x, nullptr, groups, per_frame);
@@ -349,7 +361,7 @@ int cvvae::gn_stats_run(const cvvae_tensor5* x, int32_t groups, int32_t per_fram
 }
 
 extern "C" int cvvae_groupnorm_apply(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t groups, int32_t per_frame,
-                                     const double* stats, const float* gamma, const float* beta, float eps, int32_t silu,
+                                     const int64_t* stats, const float* gamma, const float* beta, float eps, int32_t silu,
                                      int32_t dtype, void* stream_) {
   CVVAE_CHECK_ARG(tensor_ok(x) && tensor_ok(y) && stats && gamma && beta, "cvvae_groupnorm_apply: null argument");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -360,7 +372,10 @@ extern "C" int cvvae_groupnorm_apply(const cvvae_tensor5* x, const cvvae_tensor5
   dim3 grid;
   pick_grid(v, units, grid);
   const size_t smem = sizeof(float) * 2 * x->C;
-  CVVAE_DISPATCH_DTYPE(dtype, { gn_apply_kernel<DT><<<grid, 256, smem, stream>>>(v, reinterpret_cast<const long long*>(stats), gamma, beta, eps, silu); });
+  const long long* st = reinterpret_cast<const long long*>(stats);
+  // 4 loads in flight per thread + streaming (no-allocate / evict-first) accesses: 5.7 TB/s on 1.4 GB tensors, 87 % of the
+  // measured copy bandwidth (U = 8 or fewer CTAs per SM measured slower, plain ld/st 4 % slower)
+  CVVAE_DISPATCH_DTYPE(dtype, { gn_apply_kernel<DT, 4, 1><<<grid, 256, smem, stream>>>(v, st, gamma, beta, eps, silu); });
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;
 }

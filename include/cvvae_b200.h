@@ -85,7 +85,7 @@ typedef struct cvvae_conv_desc {
   int32_t dtype;            /* CVVAE_F16 / CVVAE_BF16 */
   int32_t flags;            /* CVVAE_CONV_* */
   float alpha;
-  double* gn_stats;         /* optional [B][gn_groups][2] int64 fixed point as above (of the STORED 16-bit y), accumulated:
+  int64_t* gn_stats;        /* optional [B][gn_groups][2] int64 fixed point as above (of the STORED 16-bit y), accumulated:
                                GroupNorm statistics of the consumer, produced in the conv epilogue instead of a
                                separate pass over y.  The caller zeroes it (several launches may add to it).  */
   int32_t gn_groups;
@@ -118,10 +118,10 @@ int cvvae_pack_conv_weight(const void* w_oikkk, void* w_packed, int32_t Cout, in
  *   stats workspace: int64 [B*(per_frame?T:1)][groups][2] FIXED POINT (sum * 2^20, sum of squares * 2^18): integer
  *   atomics make the accumulation order-independent, hence bit-reproducible; zeroed by cvvae_groupnorm_stats.
  */
-int cvvae_groupnorm_stats(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, double* stats,
+int cvvae_groupnorm_stats(const cvvae_tensor5* x, int32_t groups, int32_t per_frame, int64_t* stats,
                           int32_t dtype, void* stream);
 int cvvae_groupnorm_apply(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t groups, int32_t per_frame,
-                          const double* stats, const float* gamma, const float* beta, float eps,
+                          const int64_t* stats, const float* gamma, const float* beta, float eps,
                           int32_t silu, int32_t dtype, void* stream);
 
 /* LayerNorm over C for every (b,t,h,w) token: norm_t of MemoryEfficientAttnVideoBlock
