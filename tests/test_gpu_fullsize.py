@@ -49,3 +49,32 @@ def test_batch_items_are_independent():
     both = m.encode(x).latent_dist.parameters
     one = m.encode(x[1:2].contiguous()).latent_dist.parameters
     assert torch.equal(both[1:2], one)
+
+
+def test_c4_geometry_wrapper_equals_reference_assembly():
+    """720x1280 (BASELINE config 4's frame size), 33 frames = 2 temporal chunks x (2 x 3) ragged spatial tiles
+    (576/272 rows, 576/576/384 columns, two-directional blending): the wrapper's batched/ordered execution must equal
+    the reference's loop structure (oracle `_spatial_tiled` + chunk loop, modeling_vae.py:144-210,230-296) driven with
+    the SAME CUDA networks as tile functions - bit for bit."""
+    m = _model()
+    x = O.synthetic_video((1, 3, 33, 720, 1280), 9).half().cuda()
+    g = O.TileGeometry.of(O.VAEConfig(variant="sd21"))
+
+    def chunks(v, stride, fn):
+        outs = []
+        for n in range(max(1, -(-(v.shape[2] - 1) // stride))):
+            o = fn(v[:, :, n * stride:(n + 1) * stride + 1])
+            outs.append(o if n == 0 else o[:, :, 1:])
+        return torch.cat(outs, dim=2)
+
+    mom = m.encode(x).latent_dist.parameters
+    assert mom.shape == (1, 8, 9, 90, 160)
+    want = chunks(x, g.encode_chunk, lambda v: O._spatial_tiled(v, lambda t: m.encoder(t.contiguous()), g.pixel_tile,
+                                                                g.latent_tile, g.ratio, True))
+    assert torch.equal(mom, want)
+    z = mom[:, :4].contiguous()
+    rec = m.decode(z).sample
+    assert rec.shape == x.shape and torch.isfinite(rec).all()
+    want = chunks(z, g.decode_chunk, lambda v: O._spatial_tiled(v, lambda t: m.decoder(t.contiguous()), g.latent_tile,
+                                                                g.pixel_tile, g.ratio, False))
+    assert torch.equal(rec, want)
