@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
   ptx::tc_fence_before();
-  if (CG == 2) ptx::cluster_sync(); else __syncthreads();  // the peer's barriers / TMEM exist before anyone signals them
+  __syncthreads();                    // tmem_slot / barrier init visible CTA-wide
+  if (CG == 2) ptx::cluster_sync();   // the peer's barriers / TMEM exist before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (traced && threadIdx.x == 0) trc[1] = ptx::globaltimer_ns();

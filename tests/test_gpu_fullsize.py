@@ -78,3 +78,26 @@ def test_c4_geometry_wrapper_equals_reference_assembly():
     want = chunks(z, g.decode_chunk, lambda v: O._spatial_tiled(v, lambda t: m.decoder(t.contiguous()), g.latent_tile,
                                                                 g.pixel_tile, g.ratio, False))
     assert torch.equal(rec, want)
+
+
+def test_c3_sd3_bf16_chunks():
+    """BASELINE config 3: SD3-variant model, bf16, 33x512x512 = 2 temporal chunks of one (un-tiled) 512x512 tile."""
+    from cvvae_b200 import CVVAESD3Model
+    torch.manual_seed(17)
+    m = CVVAESD3Model()
+    g = torch.Generator().manual_seed(18)
+    for k, p in m.named_parameters():
+        if p.dim() == 1:
+            p.data.copy_(torch.rand(p.shape, generator=g) * (0.4 if k.endswith("bias") else 1.0) + (-0.2 if k.endswith("bias") else 0.5))
+    m = m.to(torch.bfloat16).cuda()
+    x = O.synthetic_video((1, 3, 33, 512, 512), 4).to(torch.bfloat16).cuda()
+    mom = m.encode(x).latent_dist.parameters
+    assert mom.shape == (1, 32, 9, 64, 64) and torch.isfinite(mom).all()
+    want = torch.cat([m.encoder(x[:, :, 0:17].contiguous()), m.encoder(x[:, :, 16:33].contiguous())[:, :, 1:]], dim=2)
+    assert torch.equal(mom, want)
+    z = mom[:, :16].contiguous()
+    rec = m.decode(z).sample
+    assert rec.shape == x.shape and torch.isfinite(rec).all()
+    want = torch.cat([m.decoder(z[:, :, 0:5].contiguous()), m.decoder(z[:, :, 4:9].contiguous())[:, :, 1:]], dim=2)
+    assert torch.equal(rec, want)
+    assert torch.equal(rec, m.decode(z).sample)
