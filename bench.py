@@ -348,12 +348,19 @@ def main():
                 "reference_dense_tflop_per_step": tc["ref_flops"] / args.steps / 1e12,
                 "achieved_vs_reference_count": tc["ref_flops"] / (tc["ms"] * 1e-3) / 1e12,
                 "conv_direct_ms_per_step": prof["conv_direct"]["ms"] / args.steps}
+    def _n(n, tile=576, stride=448):
+        k, i = 1, 0
+        while i + tile < n:
+            i += stride
+            k += 1
+        return k
+    n_tiles = _n(args.height) * _n(args.width)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{total_frames}x3x{args.height}x{args.width} clip, encode(x).mode() -> decode(z), "
                                    f"wrapper tiling 576/448 + 16-frame chunks; SD2.1-variant CVVAEModel, seeded random weights",
-                       "per_gpu": f"one {args.frames}-frame chunk = 2 tiles of 17x576x576", "parallelism": f"frame-shard x{world}",
+                       "per_gpu": f"one {args.frames}-frame chunk = {n_tiles} spatial tiles (<= 576x576, stride 448)", "parallelism": f"frame-shard x{world}",
                        "l2": "no explicit flush: every step streams >100 GB of activations (each up to 1.4 GB) through a 126 MB L2"},
             "impl": args.impl, "gpu_launches": launches // args.steps if launches else 0, "clocks": clocks, "e2e": e2e}
     if roof:
