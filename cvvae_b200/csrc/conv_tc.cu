@@ -1088,13 +1088,20 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     p.n_hgroups = d->KH / p.KHs;
     long long best_cost = -1;
     int best_tw = 16;
+    // CTA pairs stack two tiles vertically: an odd tile count costs one whole padding tile per column of tiles
+    const char* cg_e = getenv("CVVAE_CONV_CTA_GROUP");
+    const int cg_plan = (cg_e && atoi(cg_e) == 1) ? 1 : (((cg_e && atoi(cg_e) == 2) || N_cta == 256) ? 2 : 1);
     for (int tw = 8; tw <= 128; tw *= 2) {
       const int rows = 128 / tw;
       const int th = rows * p.NACC;
       if (tw * d->sw > 256 || (th + p.KHs - 1) * d->sh > 256) continue;
       const long long tiles_w = (p.W_out + tw - 1) / tw;
-      const long long subtiles_h = (p.H_out + rows - 1) / rows;
-      const long long tiles_h = (p.H_out + th - 1) / th;
+      long long subtiles_h = (p.H_out + rows - 1) / rows;
+      long long tiles_h = (p.H_out + th - 1) / th;
+      if (cg_plan == 2 && tiles_h >= 2 && (tiles_h & 1)) {
+        tiles_h += 1;
+        subtiles_h += p.NACC;
+      }
       // MMA work ~ sub-tiles; slab traffic ~ (th + halo) rows per tile
       const long long cost = tiles_w * subtiles_h * 128 * 16 + tiles_w * tiles_h * (th + p.KHs - 1) * tw * 3;
       if (best_cost < 0 || cost < best_cost) {
@@ -1102,6 +1109,13 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
         best_tw = tw;
       }
     }
+    static const int tw_env = [] {   // experiment knob: force the tile width
+      const char* e = getenv("CVVAE_CONV_TW");
+      return e ? atoi(e) : 0;
+    }();
+    if (tw_env >= 8 && tw_env <= 128 && (tw_env & (tw_env - 1)) == 0 && tw_env * d->sw <= 256 &&
+        ((128 / tw_env) * p.NACC + p.KHs - 1) * d->sh <= 256)
+      best_tw = tw_env;
     p.TW = best_tw;
     p.ROWS = 128 / p.TW;
     p.TH = p.ROWS * p.NACC;

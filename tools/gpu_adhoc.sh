@@ -1,4 +1,4 @@
 cd /root/repo; mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "ours exit $?"
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.log 2>&1; echo "ref exit $?"
-tail -n 1 gpurun_out/bench_reference.log | cut -c1-600
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_e2e.py -q -x 2>&1 | tail -2
+timeout 600 python tools/bench_conv.py --reps 3 2>&1 | grep '"layer"' | cut -c1-120 | tee gpurun_out/bench_conv.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200
