@@ -1,5 +1,4 @@
 cd /root/repo; mkdir -p gpurun_out
-for tw in 0 8 16 32 64 128; do
-  echo "== TW=$tw"
-  CVVAE_CONV_TW=$tw timeout 600 python tools/bench_conv.py --reps 3 2>&1 | grep '"layer"' | cut -c1-100
-done 2>&1 | tee gpurun_out/tw_sweep_all.log
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_gpu_ops.py -q -x -k "not forced" > gpurun_out/sanitize_racecheck.log 2>&1; echo "racecheck exit $?"
+grep -E "RACECHECK SUMMARY|ERROR SUMMARY|passed|failed" gpurun_out/sanitize_racecheck.log | head
+grep -E "Error: Race|and (Read|Write) access" gpurun_out/sanitize_racecheck.log | sed 's/+0x[0-9a-f]*//' | sort | uniq -c | sort -rn | head -20
