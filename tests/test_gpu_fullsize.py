@@ -101,3 +101,53 @@ def test_c3_sd3_bf16_chunks():
     want = torch.cat([m.decoder(z[:, :, 0:5].contiguous()), m.decoder(z[:, :, 4:9].contiguous())[:, :, 1:]], dim=2)
     assert torch.equal(rec, want)
     assert torch.equal(rec, m.decode(z).sample)
+
+
+@pytest.mark.parametrize("variant,dtype,shape", [("sd21", torch.float16, (1, 3, 17, 576, 1024)),
+                                                 ("sd3", torch.bfloat16, (1, 3, 33, 512, 512))])
+def test_full_size_parity_against_reference_algorithm(variant, dtype, shape):
+    """BASELINE configs 2 and 3 at full size: this engine vs the reference algorithm (oracle) run on the same GPU in fp32
+    (library kernels, TF32 off) as the gold, with the reference algorithm in the same 16-bit dtype as the yardstick:
+    error(engine, gold) <= 1.5 x error(reference-16-bit, gold) + floor, for moments and reconstruction."""
+    from cvvae_b200 import CVVAEModel, CVVAESD3Model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = O.VAEConfig(variant=variant) if variant == "sd21" else O.VAEConfig(variant="sd3", z_channels=16)
+    sd = O.make_state_dict(cfg, 4242)
+    m = (CVVAEModel() if variant == "sd21" else CVVAESD3Model())
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dtype).cuda()
+    x = O.synthetic_video(shape, 21)
+    xd = x.to(dtype).cuda()
+    post = m.encode(xd).latent_dist
+    rec = m.decode(post.mode()).sample
+    zc = cfg.z_channels
+
+    def run_ref(dt):
+        sdd = {k: v.to(dt).cuda() for k, v in sd.items()}
+        with torch.no_grad():
+            p = O.encode(xd.to(dt), sdd, cfg)
+            # decode the SAME latent the engine decoded, so that the reconstruction error is the decoder's alone
+            r = O.decode(post.mode().to(dt), sdd, cfg)
+        return p.parameters.float().cpu(), r.float().cpu()
+
+    gold_m, gold_r = run_ref(torch.float32)
+    torch.cuda.empty_cache()
+    ref_m, ref_r = run_ref(dtype)
+    torch.cuda.empty_cache()
+
+    def err(a, b):
+        d = (a - b).abs()
+        return d.max().item(), d.mean().item()
+
+    mine_m, mine_r = err(post.parameters.float().cpu(), gold_m), err(rec.float().cpu(), gold_r)
+    r_m, r_r = err(ref_m, gold_m), err(ref_r, gold_r)
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"fullsize_parity_{variant}.json"), "w") as f:
+        json.dump(dict(shape=shape, dtype=str(dtype), engine_vs_fp32=dict(moments=mine_m, recon=mine_r),
+                       reference16_vs_fp32=dict(moments=r_m, recon=r_r)), f, indent=1)
+    floor = 2e-3 if dtype == torch.float16 else 2e-2
+    assert mine_m[0] <= 1.5 * r_m[0] + floor and mine_m[1] <= 1.5 * r_m[1] + floor / 10, (mine_m, r_m)
+    assert mine_r[0] <= 1.5 * r_r[0] + floor and mine_r[1] <= 1.5 * r_r[1] + floor / 10, (mine_r, r_r)
