@@ -1145,6 +1145,13 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;
   int NA = static_cast<int>(rest / p.slab_bytes);
   if (NA > 4) NA = 4;
+  {
+    static const int na_env = [] {   // experiment knob: cap the slab ring (the rest of shared memory goes to weight slots)
+      const char* e = getenv("CVVAE_CONV_NA");
+      return e ? atoi(e) : 0;
+    }();
+    if (na_env >= 2 && na_env < NA) NA = na_env;
+  }
   CVVAE_CHECK_ARG(NA >= 2, "conv_tc: slab of %u bytes does not fit the shared-memory budget", p.slab_bytes);
   // spend what is left on more weight stages
   while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_bytes <= budget) ++NB;
