@@ -42,6 +42,10 @@ CASES = [
          shape=(1, 3, 5, 32, 32)),
     dict(name="sd21_w32_image", variant="sd21", ch=32, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None),
          shape=(2, 3, 1, 32, 48)),
+    # 4-D call convention of the wrappers: (b t) c h w in, num_video_frames / num_latent_frames regrouping, 4-D out
+    dict(name="sd21_w32_frames4d", variant="sd21", ch=32,
+         wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=4, num_video_frames=5, reshape_x_dim_to_4=True),
+         shape=(10, 3, 32, 40)),
     dict(name="sd3_w32_plain", variant="sd3", ch=32, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None),
          shape=(1, 3, 9, 64, 64)),
     dict(name="sd3_w32_tiled", variant="sd3", ch=32, wrap=dict(tile_spatial_size=72, en_de_n_frames_a_time=4),
@@ -81,6 +85,10 @@ def main():
                 # 4-D path of the SD pipelines: decode(latents, num_frames=1) (pipeline_stable_diffusion.py:1046)
                 z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, *z.shape[1:2], *z.shape[3:])
                 arrays["recon_4d"] = m.decode(z4, num_frames=1).sample.numpy()
+            if case["name"].endswith("_frames4d"):
+                # 4-D latents regrouped with the model's own num_latent_frames (modeling_vae.py:308-309)
+                z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, *z.shape[1:2], *z.shape[3:])
+                arrays["recon_4dlat"] = m.decode(z4).sample.numpy()
         np.savez(os.path.join(HERE, case["name"] + ".npz"), **arrays)
         shapes = {k: list(v) for k, v in O.param_shapes(cfg).items()}
         entry = dict(case)

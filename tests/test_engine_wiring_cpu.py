@@ -50,6 +50,10 @@ def test_engine_graph_matches_reference(name):
         z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, z.shape[1], *z.shape[3:])
         rec4 = m.decode(z4, num_frames=1).sample
         np.testing.assert_allclose(rec4.numpy(), gold["recon_4d"], rtol=1e-4, atol=5e-5)
+    if "recon_4dlat" in gold.files:
+        z = post.mode()
+        z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, z.shape[1], *z.shape[3:])
+        np.testing.assert_allclose(m.decode(z4).sample.numpy(), gold["recon_4dlat"], rtol=1e-4, atol=5e-5)
 
 
 def test_surface_matches_reference_contract(tmp_path):

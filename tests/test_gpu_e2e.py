@@ -78,6 +78,11 @@ def test_engine_vs_reference_golden(name, dtype):
     floor = 2e-3 if dtype == torch.float16 else 2e-2
     assert mine_m[0] <= 1.5 * ref_m[0] + floor and mine_m[1] <= 1.5 * ref_m[1] + floor / 10, (mine_m, ref_m)
     assert mine_r[0] <= 1.5 * ref_r[0] + floor and mine_r[1] <= 1.5 * ref_r[1] + floor / 10, (mine_r, ref_r)
+    if "recon_4dlat" in gold.files:
+        # 4-D latents regrouped by the model's num_latent_frames: must be the same computation as the 5-D call
+        z = post.mode()
+        z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, z.shape[1], *z.shape[3:])
+        assert torch.equal(m.decode(z4).sample, rec)
 
 
 def test_forward_and_4d_paths():

@@ -44,6 +44,10 @@ def test_oracle_matches_reference_outputs(name):
         z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, z.shape[1], *z.shape[3:])
         rec4 = O.decode(z4, sd, cfg, num_frames=1)
         np.testing.assert_allclose(rec4.numpy(), gold["recon_4d"], rtol=0, atol=2e-6)
+    if "recon_4dlat" in gold.files:
+        z = post.mode()
+        z4 = z.permute(0, 2, 1, 3, 4).reshape(-1, z.shape[1], *z.shape[3:])
+        np.testing.assert_allclose(O.decode(z4, sd, cfg).numpy(), gold["recon_4dlat"], rtol=0, atol=2e-6)
 
 
 @pytest.mark.parametrize("variant", ["sd21", "sd3"])
