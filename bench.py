@@ -370,6 +370,7 @@ def main():
                        "per_gpu": f"one {args.frames}-frame chunk = {n_tiles} spatial tiles (<= 576x576, stride 448)", "parallelism": f"frame-shard x{world}",
                        "l2": "no explicit flush: every step streams >100 GB of activations (each up to 1.4 GB) through a 126 MB L2"},
             "impl": args.impl, "gpu_launches": launches // args.steps if launches else 0, "clocks": clocks, "e2e": e2e}
+    line["peak_hbm_gb"] = round(torch.cuda.max_memory_allocated() / 1e9, 2)  # activations + weights + graph pools, this rank
     if roof:
         line["roofline"] = roof
     if args.impl == "ours" and not args.no_cpu_baseline and world == 1:
