@@ -1078,6 +1078,11 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   if (persist_want) p.NACC = 2;
   p.flat = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1) ? 1 : 0;
   p.cblocks = (p.Cin + 63) / 64;
+  static const int fill_env = [] {   // experiment knob: 0 keeps the widest tiles even when they leave SMs idle
+    const char* e = getenv("CVVAE_CONV_FILL");
+    return e ? atoi(e) : 1;
+  }();
+  for (;;) {
   if (p.flat) {
     p.TW = 128; p.ROWS = 1; p.TH = 1;
     p.KHs = 1; p.n_hgroups = 1; p.slab_rows = p.NACC;
@@ -1122,6 +1127,12 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     p.slab_rows = p.TH + p.KHs - 1;
     p.tiles_w = (p.W_out + p.TW - 1) / p.TW;
     p.tiles_h = (p.H_out + p.TH - 1) / p.TH;
+  }
+  // small problems (latent-resolution layers, single images, attention GEMMs): fewer accumulators per CTA = more CTAs.
+  // The count is per SAMPLE so that the plan - hence every rounding - is independent of the batch size.
+  const long long ctas_per_sample = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_h;
+  if (!fill_env || persist_want || p.NACC <= 1 || ctas_per_sample >= num_sms()) break;
+  p.NACC /= 2;
   }
   p.slab_bytes = p.flat ? static_cast<uint32_t>(p.NACC) * 16384u : static_cast<uint32_t>(p.slab_rows * p.TW) * 128u;
   // CTA pairs (cta_group::2) when there are at least two vertically adjacent tiles to pair up
