@@ -8,23 +8,25 @@ from oracle import cvvae_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _model():
-    from cvvae_b200 import CVVAEModel
+def _model(variant="sd21", dtype=torch.float16):
+    from cvvae_b200 import CVVAEModel, CVVAESD3Model
     torch.manual_seed(7)
-    m = CVVAEModel()
+    m = CVVAEModel() if variant == "sd21" else CVVAESD3Model()
     g = torch.Generator().manual_seed(8)
     for k, p in m.named_parameters():
         if p.dim() == 1:
             p.data.copy_(torch.rand(p.shape, generator=g) * (0.4 if k.endswith("bias") else 1.0) + (-0.2 if k.endswith("bias") else 0.5))
-    return m.half().cuda()
+    return m.to(dtype).cuda()
 
 
-def test_c2_shape_properties():
-    m = _model()
-    x = O.synthetic_video((1, 3, 17, 576, 1024), 5).half().cuda()
+@pytest.mark.parametrize("variant,dtype", [("sd21", torch.float16), ("sd3", torch.bfloat16)])
+def test_c2_shape_properties(variant, dtype):
+    m = _model(variant, dtype)
+    zc = 4 if variant == "sd21" else 16
+    x = O.synthetic_video((1, 3, 17, 576, 1024), 5).to(dtype).cuda()
     mom1 = m.encode(x).latent_dist.parameters
     mom2 = m.encode(x).latent_dist.parameters
-    assert mom1.shape == (1, 8, 5, 72, 128)
+    assert mom1.shape == (1, 2 * zc, 5, 72, 128)
     assert torch.equal(mom1, mom2), "encode is not deterministic"
     assert torch.isfinite(mom1).all()
     # wrapper == manual assembly: 2 tiles at w = 0 and 448, blend_h over 16 latent columns (modeling_vae.py:148-190)
@@ -33,7 +35,7 @@ def test_c2_shape_properties():
     t1 = O.blend_h(t0, t1.clone(), 16)
     manual = torch.cat([t0[:, :, :, :, :56], t1], dim=4)
     assert torch.equal(manual, mom1), "tiled encode differs from manual tile assembly"
-    z = mom1[:, :4].contiguous()
+    z = mom1[:, :zc].contiguous()
     rec1 = m.decode(z).sample
     rec2 = m.decode(z).sample
     assert rec1.shape == x.shape and torch.equal(rec1, rec2) and torch.isfinite(rec1).all()
