@@ -11,7 +11,7 @@ from ._build import LIBPATH
 
 F16, BF16 = 0, 1
 PAD_ZERO, PAD_REPLICATE = 0, 1
-CONV_BIAS_ALONG_M, CONV_FORCE_DIRECT, CONV_OUT_F32 = 1, 2, 4
+CONV_BIAS_ALONG_M, CONV_FORCE_DIRECT, CONV_OUT_F32, CONV_W_PER_BATCH, CONV_X_SHARED = 1, 2, 4, 8, 16
 ABI_VERSION = 1
 
 
@@ -52,7 +52,6 @@ _SIGNATURES = {
     "cvvae_layernorm": (C.c_int, [_P5, _P5, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
     "cvvae_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "cvvae_attn_temporal": (C.c_int, [_P5, _P5, _P5, _P5, C.c_int32, C.c_void_p]),
-    "cvvae_upsample_nearest2x": (C.c_int, [_P5, _P5, C.c_int32, C.c_void_p]),
     "cvvae_replicate_border": (C.c_int, [_P5, C.c_int32, C.c_void_p]),
     "cvvae_copy5": (C.c_int, [_P5, _P5, C.c_int32, C.c_void_p]),
     "cvvae_blend": (C.c_int, [_P5, _P5, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

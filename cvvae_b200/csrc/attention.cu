@@ -1,7 +1,7 @@
 // Attention pieces that are not GEMMs.  The GEMMs of the attention blocks (q/k/v/proj 1x1 convs, S = q k^T,
 // O = P v) run on the tcgen05 convolution kernel as 1x1x1 "flat" problems (see engine.py); here:
 //   * row softmax  fp32 logits -> 16-bit probabilities     (models/vae_models.py:456,518,607)
-//   * temporal attention over the <= 32 frames of one chunk (models/vae_models.py:573-587)
+//   * temporal attention over the latent frames of one chunk (models/vae_models.py:573-587)
 #include "common.cuh"
 
 namespace cvvae {
@@ -55,10 +55,12 @@ struct TAttnParams {
   float scale;
 };
 
-static constexpr int kMaxT = 32;
-
-template <int DT>
+// MAXT bounds the per-thread score array: 32 covers every chunked configuration (<= 5 latent frames per chunk with the
+// default 16-frame chunks); the 128 / 512 instantiations (scores in local memory) serve en_de_n_frames_a_time=None,
+// where the decoder mid-block sees every latent frame of the clip at once.
+template <int DT, int MAXT>
 __global__ void __launch_bounds__(128) attn_temporal_kernel(const TAttnParams p) {
+  constexpr int kMaxT = MAXT;
   using E = Elem<DT>;
   using T = typename E::T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,8 +140,11 @@ extern "C" int cvvae_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t
   CVVAE_CHECK_ARG(smem <= 200 * 1024, "cvvae_softmax_rows: %d columns exceed the shared-memory row cache", cols);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CVVAE_DISPATCH_DTYPE(dtype, {
-    if (smem > 48 * 1024)
+    static PerDeviceOnce attr;
+    if (smem > 48 * 1024 && attr.need()) {
       CVVAE_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr.mark();
+    }
     softmax_rows_kernel<DT><<<static_cast<unsigned>(rows), 256, smem, stream>>>(s, ld_s, p, ld_p, cols);
   });
   CVVAE_LAUNCH_CHECK();
@@ -149,7 +154,7 @@ extern "C" int cvvae_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t
 extern "C" int cvvae_attn_temporal(const cvvae_tensor5* q, const cvvae_tensor5* k, const cvvae_tensor5* v,
                                    const cvvae_tensor5* o, int32_t dtype, void* stream_) {
   CVVAE_CHECK_ARG(tensor_ok(q) && tensor_ok(k) && tensor_ok(v) && tensor_ok(o), "cvvae_attn_temporal: null argument");
-  CVVAE_CHECK_ARG(q->T <= kMaxT, "cvvae_attn_temporal: %d frames per chunk > %d unsupported", q->T, kMaxT);
+  CVVAE_CHECK_ARG(q->T <= 512, "cvvae_attn_temporal: %d latent frames in one chunk > 512 unsupported (use temporal chunking)", q->T);
   CVVAE_CHECK_ARG(q->C % 8 == 0, "cvvae_attn_temporal: C %% 8 != 0");
   const cvvae_tensor5* ts[4] = {q, k, v, o};
   for (int i = 0; i < 4; ++i) {
@@ -170,7 +175,11 @@ extern "C" int cvvae_attn_temporal(const cvvae_tensor5* q, const cvvae_tensor5* 
   const long long blocks = (npos + 3) / 4;
   CVVAE_CHECK_ARG(blocks < (1ll << 31), "cvvae_attn_temporal: too many positions");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CVVAE_DISPATCH_DTYPE(dtype, { attn_temporal_kernel<DT><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(p); });
+  CVVAE_DISPATCH_DTYPE(dtype, {
+    if (q->T <= 32) attn_temporal_kernel<DT, 32><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(p);
+    else if (q->T <= 128) attn_temporal_kernel<DT, 128><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(p);
+    else attn_temporal_kernel<DT, 512><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(p);
+  });
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;
 }

@@ -110,16 +110,32 @@ __device__ __forceinline__ unsigned long long gn_fix(float v, double scale) {
 // x * sigmoid(x); fast reciprocal (2 ulp) is far below the 16-bit output rounding
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// ---- per-device state.  The library may be driven on several GPUs from one process (a model per device): everything
+// cached about "the device" is keyed by the CURRENT device ordinal at the time of the call (the caller guarantees the
+// current device is the one the pointers live on; cvvae_b200/ops.py enforces that).
+constexpr int kMaxDevices = 64;
+inline int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+inline int num_sms() {
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = cur_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// "has this one-time set-up (cudaFuncSetAttribute ...) been done on the current device?"  One static instance per call site.
+struct PerDeviceOnce {
+  std::atomic<bool> done[kMaxDevices];
+  bool need() const { return !done[cur_device()].load(std::memory_order_acquire); }
+  void mark() { done[cur_device()].store(true, std::memory_order_release); }
+};
 
 inline bool tensor_ok(const cvvae_tensor5* t) {
   return t && t->ptr && t->B > 0 && t->T > 0 && t->H > 0 && t->W > 0 && t->C > 0;

@@ -257,10 +257,10 @@ extern "C" int cvvae_conv3d_stacked(const cvvae_conv_desc* d, void* stream_) {
   const size_t smem = 1024 + kNA * kSlabBytes + kNB * kBBytes + 256;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CVVAE_DISPATCH_DTYPE(d->dtype, {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
       CVVAE_CUDA(cudaFuncSetAttribute(conv_stk_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
+      attr.mark();
     }
     conv_stk_kernel<DT><<<static_cast<unsigned>(grid), 256, smem, stream>>>(tmA, tmB, p);
   });

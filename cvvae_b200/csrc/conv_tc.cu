@@ -21,6 +21,7 @@
 // Replaces cuDNN behind CausalConv3d / nn.Conv3d / Conv2dWithExtraDim / Downsample3D / Upsample3D
 // (reference: models/vae_models.py:198-340, models/vae_blocks3d_sd3.py:16-364); see include/cvvae_b200.h.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     {
       int slot = 0;
       uint32_t phase = 0;
+      const int xb = (p.flags & CVVAE_CONV_X_SHARED) ? 0 : tc.b;  // batched GEMM with one shared left operand
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&emptyA[slot], phase ^ 1);
         uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_bytes;
@@ -179,16 +181,16 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (p.flat) {
             ptx::mbar_expect_tx(&fullA[slot], static_cast<uint32_t>(nacc_eff) * 128u * 128u);
             for (int s = 0; s < nacc_eff; ++s)
-              ptx::tma_load_5d(dst + s * 16384, &tmA, &fullA[slot], cb * 64, tc.w0 + s * 128, 0, ti, tc.b);
+              ptx::tma_load_5d(dst + s * 16384, &tmA, &fullA[slot], cb * 64, tc.w0 + s * 128, 0, ti, xb);
           } else if (CG == 2) {
             // both CTAs' bytes complete on the leader's barrier
             if (rank == 0) ptx::mbar_expect_tx(&fullA[slot], 2u * p.slab_bytes);
             ptx::tma_load_5d_cg2(dst, &tmA, ptx::mapa_u32(ptx::smem_u32(&fullA[slot]), 0), cb * 64,
-                                 tc.w0 * p.sw + kw + p.off_w, tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
+                                 tc.w0 * p.sw + kw + p.off_w, tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, xb);
           } else {
             ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
             ptx::tma_load_5d(dst, &tmA, &fullA[slot], cb * 64, tc.w0 * p.sw + kw + p.off_w,
-                             tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
+                             tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, xb);
           }
         }
         __syncwarp();
@@ -205,7 +207,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         for (int khs = 0; khs < p.KHs; ++khs) {
-          const int tap = (kt * p.KH + hg * p.KHs + khs) * p.KW + kw;
+          // batched GEMM: the "tap" axis of the weight tensor indexes the batch item (1x1x1 problems only)
+          const int tap = (p.flags & CVVAE_CONV_W_PER_BATCH) ? tc.b : (kt * p.KH + hg * p.KHs + khs) * p.KW + kw;
           wait_bar(&emptyB[slot], phase ^ 1);
           if (ptx::elect_one()) {
             if (CG == 2) {
@@ -326,6 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     ptx::tc_fence_after();
     if (traced && threadIdx.x == 128) trc[5] = ptx::globaltimer_ns();
     const int chalf = p.up_time == 2 ? p.Cout / 2 : p.Cout;
+    const int bias_b = (p.flags & CVVAE_CONV_W_PER_BATCH) ? 0 : tc.b;  // batched GEMM: a row bias is shared by the batch items
     int item = 0;
     if (p.tma_epi && p.swap) {
       // ---- swapped orientation: this thread owns output channel c = 32q + lane, a 32x32b TMEM load gives it 32
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         float bias_m = 0.f;
         if (p.bias && (p.flags & CVVAE_CONV_BIAS_ALONG_M)) {
           const long long m_index =
-              ((static_cast<long long>(tc.b) * p.T_out + tc.t) * p.H_out + h_me) * static_cast<long long>(p.W_out) + w_me;
+              ((static_cast<long long>(bias_b) * p.T_out + tc.t) * p.H_out + h_me) * static_cast<long long>(p.W_out) + w_me;
           if (h_me < p.H_out && w_me < p.W_out) bias_m = __ldg(p.bias + m_index);
         }
         for (int c0 = 0; c0 < p.N_cta; c0 += 64) {
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       const bool pix_ok = (h < p.H_out) && (w < p.W_out);
       const long long m_index =
-          ((static_cast<long long>(tc.b) * p.T_out + tc.t) * p.H_out + h) * static_cast<long long>(p.W_out) + w;
+          ((static_cast<long long>(bias_b) * p.T_out + tc.t) * p.H_out + h) * static_cast<long long>(p.W_out) + w;
       for (int c0 = 0; c0 < p.N_cta; c0 += 32) {
         const int cg0 = tc.n0 + c0;
         if (cg0 >= p.Cout) break;  // warp-uniform
@@ -952,9 +956,48 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
 }
 
 // ---------------------------------------------------------------------------------------- host side
+// cuTensorMapEncodeTiled is a pure function of its arguments and costs 1-2 us on the host; a network pass issues the same
+// few hundred (pointer, shape) combinations call after call (the activation buffers come back from the caching allocator at
+// the same addresses), so the encoded maps are memoised per thread, keyed by the full argument list ("optional
+// descriptor cache keyed by (ptr, shape)").
+struct TmapKey {
+  const void* ptr;
+  uint32_t rank, swizzle;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+static constexpr int kTmapSlots = 1024;
+
 static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
                        const cuuint32_t* box, const cuuint32_t* estr,
                        CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  static thread_local TmapSlot* cache = nullptr;
+  if (!cache) cache = static_cast<TmapSlot*>(calloc(kTmapSlots, sizeof(TmapSlot)));
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr;
+  key.rank = static_cast<uint32_t>(rank);
+  key.swizzle = static_cast<uint32_t>(swizzle);
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    key.estr[i] = estr[i];
+    if (i + 1 < rank) key.strides[i] = strides_b[i];
+  }
+  uint64_t h = 1469598103934665603ull;  // FNV-1a over the key bytes
+  const unsigned char* kb = reinterpret_cast<const unsigned char*>(&key);
+  for (size_t i = 0; i < sizeof(key); ++i) h = (h ^ kb[i]) * 1099511628211ull;
+  TmapSlot* slot = cache ? &cache[h % kTmapSlots] : nullptr;
+  if (slot && slot->valid && slot->key == key) {
+    *m = slot->map;
+    return true;
+  }
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -971,7 +1014,29 @@ static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64
               rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
     return false;
   }
+  if (slot) {
+    slot->key = key;
+    slot->map = *m;
+    slot->valid = true;
+  }
   return true;
+}
+
+// Experiment knobs (environment), read ONCE per process - nothing on the launch path calls getenv.
+struct Knobs {
+  int nacc, persist, fill, cta_group, tw, na, swap;
+  static int env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+  }
+  Knobs()
+      : nacc(env("CVVAE_CONV_NACC", 0)), persist(env("CVVAE_CONV_PERSIST", 1)), fill(env("CVVAE_CONV_FILL", 1)),
+        cta_group(env("CVVAE_CONV_CTA_GROUP", 0)), tw(env("CVVAE_CONV_TW", 0)), na(env("CVVAE_CONV_NA", 0)),
+        swap(env("CVVAE_CONV_SWAP", 1)) {}
+};
+static const Knobs& knobs() {
+  static const Knobs k;
+  return k;
 }
 
 bool conv_tc_eligible(const cvvae_conv_desc* d, const char** why) {
@@ -1035,7 +1100,11 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.trace = g_trace_buf;
   p.trace_n = g_trace_n;
   p.bias_vec = d->bias && (reinterpret_cast<uintptr_t>(d->bias) % 16 == 0);
-  CVVAE_CHECK_ARG(y.B == x.B, "conv: batch mismatch");
+  if (d->flags & CVVAE_CONV_X_SHARED) CVVAE_CHECK_ARG(x.B == 1, "conv: CVVAE_CONV_X_SHARED needs x.B == 1");
+  else CVVAE_CHECK_ARG(y.B == x.B, "conv: batch mismatch");
+  if (d->flags & CVVAE_CONV_W_PER_BATCH)
+    CVVAE_CHECK_ARG(d->KT * d->KH * d->KW == 1 && p.up_time == 1 && !d->gn_stats, "conv: per-batch weights need a 1x1x1 problem");
+  p.B = y.B;
   CVVAE_CHECK_ARG(y.C == (p.up_time == 2 ? d->Cout / 2 : d->Cout), "conv: y.C %d inconsistent with Cout %d / up_time %d",
                   y.C, d->Cout, p.up_time);
   p.vec_ok = (y.s_c == 1) && (y.s_w % 8 == 0) && (y.s_h % 8 == 0) && (y.s_t % 8 == 0) && (y.s_b % 8 == 0) &&
@@ -1059,29 +1128,20 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.N_cta = N_cta;
   p.n_tiles_n = (p.Cout + N_cta - 1) / N_cta;
   p.NACC = (512 / N_cta) < 4 ? (512 / N_cta) : 4;
-  {
-    // experiment knob: fewer accumulators per CTA (halves the reuse of each staged weight tile)
-    static const int nacc_env = [] {
-      const char* e = getenv("CVVAE_CONV_NACC");
-      return e ? atoi(e) : 0;
-    }();
-    if (nacc_env > 0 && nacc_env < p.NACC) p.NACC = nacc_env;
-  }
+  const Knobs& kn = knobs();
+  // experiment knob: fewer accumulators per CTA (halves the reuse of each staged weight tile)
+  if (kn.nacc > 0 && kn.nacc < p.NACC) p.NACC = kn.nacc;
   // persistent double-buffered variant for the Cout == 128 layers: tiles of 256 positions (two 128-row sub-tiles)
-  static const int persist_env = [] {
-    const char* e = getenv("CVVAE_CONV_PERSIST");
-    return e ? atoi(e) : 1;
-  }();
+  const int persist_env = kn.persist;
   const bool flat_shape = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1);
   const bool persist_want = persist_env && !flat_shape && p.Cout == 128 && N_cta == 128 && p.up_time == 1 && p.vec_ok &&
                             !(d->flags & (CVVAE_CONV_BIAS_ALONG_M | CVVAE_CONV_OUT_F32)) && y.C % 32 == 0;
   if (persist_want) p.NACC = 2;
   p.flat = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1) ? 1 : 0;
+  if (d->flags & (CVVAE_CONV_W_PER_BATCH | CVVAE_CONV_X_SHARED))
+    CVVAE_CHECK_ARG(p.flat, "conv: batched-GEMM flags need a flat problem (H == 1, 1x1x1, stride 1)");
   p.cblocks = (p.Cin + 63) / 64;
-  static const int fill_env = [] {   // experiment knob: 0 keeps the widest tiles even when they leave SMs idle
-    const char* e = getenv("CVVAE_CONV_FILL");
-    return e ? atoi(e) : 1;
-  }();
+  const int fill_env = kn.fill;   // experiment knob: 0 keeps the widest tiles even when they leave SMs idle
   for (;;) {
   if (p.flat) {
     p.TW = 128; p.ROWS = 1; p.TH = 1;
@@ -1094,8 +1154,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     long long best_cost = -1;
     int best_tw = 16;
     // CTA pairs stack two tiles vertically: an odd tile count costs one whole padding tile per column of tiles
-    const char* cg_e = getenv("CVVAE_CONV_CTA_GROUP");
-    const int cg_plan = (cg_e && atoi(cg_e) == 1) ? 1 : (((cg_e && atoi(cg_e) == 2) || N_cta == 256) ? 2 : 1);
+    const int cg_plan = kn.cta_group == 1 ? 1 : ((kn.cta_group == 2 || N_cta == 256) ? 2 : 1);
     for (int tw = 8; tw <= 128; tw *= 2) {
       const int rows = 128 / tw;
       const int th = rows * p.NACC;
@@ -1114,10 +1173,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
         best_tw = tw;
       }
     }
-    static const int tw_env = [] {   // experiment knob: force the tile width
-      const char* e = getenv("CVVAE_CONV_TW");
-      return e ? atoi(e) : 0;
-    }();
+    const int tw_env = kn.tw;   // experiment knob: force the tile width
     if (tw_env >= 8 && tw_env <= 128 && (tw_env & (tw_env - 1)) == 0 && tw_env * d->sw <= 256 &&
         ((128 / tw_env) * p.NACC + p.KHs - 1) * d->sh <= 256)
       best_tw = tw_env;
@@ -1136,10 +1192,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   }
   p.slab_bytes = p.flat ? static_cast<uint32_t>(p.NACC) * 16384u : static_cast<uint32_t>(p.slab_rows * p.TW) * 128u;
   // CTA pairs (cta_group::2) when there are at least two vertically adjacent tiles to pair up
-  static const int cg_env = [] {
-    const char* e = getenv("CVVAE_CONV_CTA_GROUP");
-    return e ? atoi(e) : 0;
-  }();
+  const int cg_env = kn.cta_group;
   // measured (tools/bench_conv.py): pairs help the N_cta = 256 layers (half the weight bytes per CTA, up to +10 %)
   // and cost 0-16 % on the N_cta = 128 layers, so they are on for N_cta = 256 only (CVVAE_CONV_CTA_GROUP=2 forces them
   // wherever possible, =1 switches them off)
@@ -1156,13 +1209,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;
   int NA = static_cast<int>(rest / p.slab_bytes);
   if (NA > 4) NA = 4;
-  {
-    static const int na_env = [] {   // experiment knob: cap the slab ring (the rest of shared memory goes to weight slots)
-      const char* e = getenv("CVVAE_CONV_NA");
-      return e ? atoi(e) : 0;
-    }();
-    if (na_env >= 2 && na_env < NA) NA = na_env;
-  }
+  if (kn.na >= 2 && kn.na < NA) NA = kn.na;   // experiment knob: cap the slab ring (the rest goes to weight slots)
   CVVAE_CHECK_ARG(NA >= 2, "conv_tc: slab of %u bytes does not fit the shared-memory budget", p.slab_bytes);
   // spend what is left on more weight stages
   while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_bytes <= budget) ++NB;
@@ -1191,7 +1238,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     if (!encode_map(&tmA, x.ptr, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
   }
   {
-    const int taps = d->KT * d->KH * d->KW;
+    const int taps = (d->flags & CVVAE_CONV_W_PER_BATCH) ? x.B > y.B ? x.B : y.B : d->KT * d->KH * d->KW;
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)taps};
     const cuuint64_t wld = d->w_ld ? (cuuint64_t)d->w_ld : (cuuint64_t)p.Cin;
     cuuint64_t strides[2] = {wld * 2, wld * p.Cout * 2};
@@ -1217,10 +1264,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
       if (d->residual && !encode_map(&tmR, d->residual, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
       p.tma_epi = 1;
       // Cout == 128 layers: swap the MMA operands (see the issue loop) - needs the TMA epilogue's transposing stage
-      static const int swap_env = [] {
-        const char* e = getenv("CVVAE_CONV_SWAP");
-        return e ? atoi(e) : 1;
-      }();
+      const int swap_env = kn.swap;
       p.swap = (swap_env && !p.flat && CG == 1 && p.Cout == 128 && N_cta == 128 && (p.NACC == 4 || p.NACC == 2) && p.up_time == 1 &&
                 !(d->flags & CVVAE_CONV_BIAS_ALONG_M)) ? 1 : 0;
       if (p.swap) {
@@ -1251,18 +1295,14 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_hp * p.B * CG;
   CVVAE_CHECK_ARG(grid > 0 && grid < (1ll << 31), "conv_tc: grid size %lld out of range", grid);
   CVVAE_DISPATCH_DTYPE(d->dtype, {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;   // the > 48 KB shared-memory opt-in is per device
+    if (attr_set.need()) {
       CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
       CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<DT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-      attr_set = true;
+      CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_psw_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_set.mark();
     }
     if (p.persist) {
-      static bool pattr = false;
-      if (!pattr) {
-        CVVAE_CUDA(cudaFuncSetAttribute(conv_tc_psw_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        pattr = true;
-      }
       p.n_tiles = static_cast<int>(grid);
       const int ctas = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
       conv_tc_psw_kernel<DT><<<ctas, kPersistThreads, smem, stream>>>(tmA, tmB, tmY, tmR, p);

@@ -252,11 +252,12 @@ static int fill_view(GnView& v, const cvvae_tensor5* x, const cvvae_tensor5* y, 
 }
 
 static void pick_grid(GnView& v, int units, dim3& grid) {
-  // aim for ~8 CTAs per SM over the whole launch, at least 256 positions per CTA
-  const long long target_blocks = 8ll * num_sms();
-  long long per_unit = (target_blocks + units - 1) / units;
-  if (per_unit < 1) per_unit = 1;
-  long long ppb = (v.pix_per_unit + per_unit - 1) / per_unit;
+  // Positions per CTA depend on the per-unit extent ONLY (not on the batch size, not on the SM count of the device): the
+  // fp32 per-thread partial sums of gn_stats_kernel group the same way whether a clip runs alone, in a tile batch or on
+  // another GPU, so tile batching and sharding stay bit-identical at any size.  ~1184 CTAs per unit (8 per SM of a
+  // 148-SM part), at least 256 positions each.
+  constexpr long long kBlocksPerUnit = 1184;
+  long long ppb = (v.pix_per_unit + kBlocksPerUnit - 1) / kBlocksPerUnit;
   if (ppb < 256) ppb = 256;
   v.pix_per_block = ppb;
   grid = dim3(static_cast<unsigned>((v.pix_per_unit + ppb - 1) / ppb), static_cast<unsigned>(units));

@@ -1,5 +1,5 @@
-// Data-movement kernels either side of the convolutions: nearest x2 upsample, replicate border fill of
-// pre-padded buffers, generic strided copy, and the tile blend of the wrapper.  All HBM-bound,
+// Data-movement kernels either side of the convolutions: replicate border fill of pre-padded buffers, generic strided
+// copy (with a vectorised row path for the wrapper's tile assembly), and the tile blend of the wrapper.  All HBM-bound,
 // coalesced on the channel axis, 128-bit accesses where the layout allows.
 #include "common.cuh"
 
@@ -15,25 +15,6 @@ static V5 mk(const cvvae_tensor5* t) { return V5{t->ptr, t->B, t->T, t->H, t->W,
 static bool vec8_ok(const cvvae_tensor5* t) {
   return t->s_c == 1 && t->C % 8 == 0 && t->s_w % 8 == 0 && t->s_h % 8 == 0 && t->s_t % 8 == 0 && t->s_b % 8 == 0 &&
          reinterpret_cast<uintptr_t>(t->ptr) % 16 == 0;
-}
-
-// y[b,t,2h+i,2w+j,:] = x[b,t,h,w,:]   (F.interpolate(scale=(1,2,2), mode="nearest"))
-__global__ void __launch_bounds__(256) upsample2x_kernel(const V5 x, const V5 y) {
-  const int vecs = x.C >> 3;
-  const long long n = 1ll * y.B * y.T * y.H * y.W * vecs;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int vi = static_cast<int>(i % vecs);
-    long long r = i / vecs;
-    const int w = static_cast<int>(r % y.W); r /= y.W;
-    const int h = static_cast<int>(r % y.H); r /= y.H;
-    const int t = static_cast<int>(r % y.T); r /= y.T;
-    const int b = static_cast<int>(r);
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x.ptr) + b * x.s_b + t * x.s_t +
-                                                      (h >> 1) * x.s_h + (w >> 1) * x.s_w) + vi;
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y.ptr) + b * y.s_b + t * y.s_t + h * y.s_h + w * y.s_w) + vi;
-    *dst = __ldg(src);
-  }
 }
 
 // frame of a pre-padded buffer <- nearest interior position
@@ -90,6 +71,27 @@ __global__ void __launch_bounds__(256) copy5_kernel(const V5 x, const V5 y) {
   }
 }
 
+// Both views contiguous along W (two NCDHW tensors described as [B,T,H,W,C] with s_w == 1): the wrapper's tile assembly
+// - a cropped tile result copied into its window of the pre-allocated clip (modeling_vae.py:181-191,267-277,207-210).
+// Rows are W contiguous 16-bit elements; 128-bit accesses when both rows are 16-byte aligned, else element-wise.
+__global__ void __launch_bounds__(256) copy_rows_kernel(const V5 x, const V5 y, int vec) {
+  const int wv = vec ? y.W >> 3 : y.W;           // work items per row
+  const long long n = 1ll * y.B * y.C * y.T * y.H * wv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int w = static_cast<int>(r % wv); r /= wv;
+    const int h = static_cast<int>(r % y.H); r /= y.H;
+    const int t = static_cast<int>(r % y.T); r /= y.T;
+    const int c = static_cast<int>(r % y.C); r /= y.C;
+    const int b = static_cast<int>(r);
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(x.ptr) + b * x.s_b + t * x.s_t + h * x.s_h + c * x.s_c;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(y.ptr) + b * y.s_b + t * y.s_t + h * y.s_h + c * y.s_c;
+    if (vec) reinterpret_cast<uint4*>(dst)[w] = __ldg(reinterpret_cast<const uint4*>(src) + w);
+    else dst[w] = src[w];
+  }
+}
+
 // b[.., i ..] = (1 - i/ov) * a[.., La-ov+i ..] + (i/ov) * b[.., i ..], fp32 math, one rounding
 template <int DT>
 __global__ void __launch_bounds__(256) blend_kernel(const V5 a, const V5 b, int ov, int axis) {
@@ -139,18 +141,6 @@ static unsigned grid_for(long long n) {
 
 using namespace cvvae;
 
-extern "C" int cvvae_upsample_nearest2x(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream) {
-  (void)dtype;
-  CVVAE_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "cvvae_upsample_nearest2x: null argument");
-  CVVAE_CHECK_ARG(y->B == x->B && y->T == x->T && y->H == 2 * x->H && y->W == 2 * x->W && y->C == x->C,
-                  "cvvae_upsample_nearest2x: shape mismatch");
-  CVVAE_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "cvvae_upsample_nearest2x: needs 16-byte aligned channels-last views");
-  const long long n = 1ll * y->B * y->T * y->H * y->W * (y->C / 8);
-  upsample2x_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(x), mk(y));
-  CVVAE_LAUNCH_CHECK();
-  return CVVAE_OK;
-}
-
 extern "C" int cvvae_replicate_border(const cvvae_tensor5* xpad, int32_t dtype, void* stream) {
   (void)dtype;
   CVVAE_CHECK_ARG(tensor_ok(xpad) && xpad->H >= 3 && xpad->W >= 3, "cvvae_replicate_border: bad argument");
@@ -166,6 +156,15 @@ extern "C" int cvvae_copy5(const cvvae_tensor5* x, const cvvae_tensor5* y, int32
   CVVAE_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "cvvae_copy5: null argument");
   CVVAE_CHECK_ARG(y->B == x->B && y->T == x->T && y->H == x->H && y->W == x->W && y->C >= x->C, "cvvae_copy5: shape mismatch");
   const long long n = 1ll * y->B * y->T * y->H * y->W * y->C;
+  if (x->s_w == 1 && y->s_w == 1 && x->C == y->C && y->W > 1) {
+    auto al8 = [](const cvvae_tensor5* t) {
+      return t->s_h % 8 == 0 && t->s_t % 8 == 0 && t->s_b % 8 == 0 && t->s_c % 8 == 0 && reinterpret_cast<uintptr_t>(t->ptr) % 16 == 0;
+    };
+    const int vec = (y->W % 8 == 0 && al8(x) && al8(y)) ? 1 : 0;
+    copy_rows_kernel<<<grid_for(vec ? n / 8 : n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(x), mk(y), vec);
+    CVVAE_LAUNCH_CHECK();
+    return CVVAE_OK;
+  }
   copy5_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(x), mk(y));
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;

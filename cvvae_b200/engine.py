@@ -115,6 +115,42 @@ class Engine:
         self.dtype = dtype
         self.sd3 = cfg.variant == "sd3"
         self.hw_mode = PAD_REPLICATE if self.sd3 else PAD_ZERO
+        self._stats_arena = None   # [slots, B, groups, 2] int64, zeroed once per network pass
+        self._stats_next = 0
+        self.attn_scratch_bytes = 4 << 30  # cap of the fp32 logits buffer of the batched spatial attention
+
+    # ------------------------------------------------------------------ shape arithmetic
+    def encoded_frames(self, T: int) -> int:
+        """Latent frames the encoder yields for T pixel frames (time stride 2 at the even levels, pads (2,0) / (1,1))."""
+        for lvl in range(len(self.cfg.widths) - 1):
+            if lvl % 2 == 0:
+                T = (T - 1) // 2 + 1
+        return T
+
+    def decoded_frames(self, T: int) -> int:
+        """Pixel frames the decoder yields for T latent frames (up_time 2 -> 2T-1 at the same levels, mirrored)."""
+        L = len(self.cfg.widths)
+        for i in range(L - 1):
+            lvl = L - 1 - i
+            if ((i % 2 == 0) if self.sd3 else (lvl % 2 == 1)):
+                T = 2 * T - 1
+        return T
+
+    # ------------------------------------------------------------------ GroupNorm-sum accumulators
+    _STATS_SLOTS = 96  # >= convolutions with fused statistics in one encoder / decoder pass (sd21 decoder: 49)
+
+    def _begin_pass(self, B: int, device) -> None:
+        """One zeroed accumulator arena per network pass (one fill kernel instead of one per convolution)."""
+        self._stats_arena = self.ops.new_stats(self._STATS_SLOTS * B, self.cfg.groups, device).view(
+            self._STATS_SLOTS, B, self.cfg.groups, 2)
+        self._stats_next = 0
+
+    def new_stats(self, B: int, device) -> torch.Tensor:
+        a = self._stats_arena
+        if a is None or a.shape[1] != B or a.device != device or self._stats_next >= a.shape[0]:
+            return self.ops.new_stats(B, self.cfg.groups, device)
+        self._stats_next += 1
+        return a[self._stats_next - 1]
 
     # ------------------------------------------------------------------ primitives
     def _tc_ok(self, x: torch.Tensor) -> bool:
@@ -194,24 +230,18 @@ class Engine:
                     and all(st_ % 8 == 0 for st_ in out.stride()[:4]))
         if (want_stats or stats is not None) and stats_ok:
             if stats is None:
-                stats = self.ops.new_stats(B, self.cfg.groups, x.device)
+                stats = self.new_stats(B, x.device)
         else:
             stats = None
         skw = dict(gn_stats=stats, gn_groups=self.cfg.groups) if stats is not None else {}
-        if flat and stats is not None and B > 1:
-            # one flat GEMM per sample so that the epilogue's GroupNorm sums stay per sample (and results do not
-            # depend on how many clips share a batch)
+        if flat:
+            # a 1x1x1 convolution is a plain GEMM over the positions of each sample: [B, 1, 1, T*H*W, C] keeps the
+            # samples on the batch axis, so the tile plan, every rounding and the epilogue's per-sample GroupNorm
+            # sums are the same whether a clip runs alone or in a batch
             P = T * H * W
-            for bi in range(B):
-                self.ops.conv(x[bi].view(1, 1, 1, P, x.shape[4]), w, b, kernel=kernel,
-                              residual=residual[bi].view(1, 1, 1, P, Co) if residual is not None else None,
-                              out=out[bi].view(1, 1, 1, P, Co), gn_stats=stats[bi:bi + 1], gn_groups=self.cfg.groups)
-        elif flat:
-            P = B * T * H * W
-            xf = x.view(1, 1, 1, P, x.shape[4])
-            of = out.view(1, 1, 1, P, Co)
-            rf = residual.view(1, 1, 1, P, Co) if residual is not None else None
-            self.ops.conv(xf, w, b, kernel=kernel, residual=rf, out=of, **skw)
+            self.ops.conv(x.view(B, 1, 1, P, x.shape[4]), w, b, kernel=kernel,
+                          residual=residual.view(B, 1, 1, P, Co) if residual is not None else None,
+                          out=out.view(B, 1, 1, P, Co), **skw)
         else:
             self.ops.conv(x, w, b, kernel=kernel, stride=stride, offset=off, pad_t=pad_t, pad_hw=pad_hw,
                           up_time=up_time, residual=residual, out=out, ref_taps=ref_taps, **skw)
@@ -290,32 +320,36 @@ class Engine:
     def spatial_attention(self, hn: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v_name: str) -> torch.Tensor:
         """softmax(q k^T / sqrt(C)) v per frame, one head (vae_models.py:446-461,500-528; diffusers Attention).
 
-        Three tensor-core GEMMs per frame on the convolution kernel (1x1x1 'flat' problems):
-          v^T = W_v hn^T + b_v   (bias along rows; gives the K-major B operand of the last GEMM directly)
+        Three BATCHED tensor-core GEMMs (batch = the B*T frames, 1x1x1 'flat' problems of the convolution kernel with
+        one right operand per frame) and one row softmax over all frames:
+          v^T = W_v hn^T + b_v   (left operand W_v shared by the frames, bias along rows; gives the K-major operand of
+                                  the last GEMM directly)
           S   = q k^T * C^-0.5   (fp32 logits) ; P = softmax(S) (16 bit)
           O   = P v
+        Frames are processed in groups so that the fp32 logits stay below `attn_scratch_bytes`.
         """
         ops = self.ops
         B, T, H, W, Cc = hn.shape
-        N = H * W
+        F, N = B * T, H * W
         ld = (N + 7) // 8 * 8
         wv, bv = self.p[v_name + ".weight"], self.p[v_name + ".bias"]
         out = ops.empty((B, T, H, W, Cc), hn.dtype, hn.device)
         wv_act = wv.view(1, 1, 1, Cc, Cc)
-        vT = ops.empty((Cc, ld), hn.dtype, hn.device)
-        S = torch.empty((N, ld), dtype=torch.float32, device=hn.device)
-        P = ops.empty((N, ld), hn.dtype, hn.device)
         scale = float(Cc) ** -0.5
-        for b in range(B):
-            for t in range(T):
-                hf = hn[b, t].reshape(N, Cc)
-                qf = q[b, t].reshape(1, 1, 1, N, Cc)
-                kf = k[b, t].reshape(1, N, Cc)
-                ops.conv(wv_act, hf.view(1, N, Cc), bv, bias_along_m=True, out=vT[:, :N].unsqueeze(0).unsqueeze(0).unsqueeze(0))
-                ops.conv(qf, kf, None, alpha=scale, out_f32=True, out=S[:, :N].unsqueeze(0).unsqueeze(0).unsqueeze(0))
-                ops.softmax_rows(S, N, P)
-                ops.conv(P[:, :N].unsqueeze(0).unsqueeze(0).unsqueeze(0), vT[:, :N].unsqueeze(0), None, w_ld=ld, cout=Cc,
-                         out=out[b, t].reshape(1, 1, 1, N, Cc))
+        fg = max(1, min(F, self.attn_scratch_bytes // max(1, N * ld * 4)))
+        vT = ops.empty((fg, Cc, ld), hn.dtype, hn.device)
+        S = torch.empty((fg, N, ld), dtype=torch.float32, device=hn.device)
+        P = ops.empty((fg, N, ld), hn.dtype, hn.device)
+        hf, qf, kf, of = (t.reshape(F, N, Cc) for t in (hn, q, k, out))
+        for f0 in range(0, F, fg):
+            n = min(fg, F - f0)
+            ops.conv(wv_act, hf[f0:f0 + n], bv, bias_along_m=True, x_shared=True, w_per_batch=True, cout=N,
+                     out=vT[:n, :, :N].unsqueeze(1).unsqueeze(1))
+            ops.conv(qf[f0:f0 + n].view(n, 1, 1, N, Cc), kf[f0:f0 + n], None, alpha=scale, out_f32=True, w_per_batch=True,
+                     cout=N, out=S[:n, :, :N].unsqueeze(1).unsqueeze(1))
+            ops.softmax_rows(S[:n].view(n * N, ld), N, P[:n].view(n * N, ld))
+            ops.conv(P[:n, :, :N].unsqueeze(1).unsqueeze(1), vT[:n], None, w_ld=ld, cout=Cc, w_per_batch=True,
+                     out=of[f0:f0 + n].view(n, 1, 1, N, Cc))
         return out
 
     def attn_sd21(self, a: Act, p: str, attn_type: str) -> Act:
@@ -357,6 +391,7 @@ class Engine:
         causal = cfg.causal_encoder
         L = len(cfg.widths)
         a = Act(x.permute(0, 2, 3, 4, 1))
+        self._begin_pass(x.shape[0], x.device)
         E = "encoder."
         h = self.conv3(a, E + "conv_in", causal, want_stats=True)
         for lvl in range(L):
@@ -397,6 +432,7 @@ class Engine:
         L = len(cfg.widths)
         D = "decoder."
         a = Act(z.permute(0, 2, 3, 4, 1))
+        self._begin_pass(z.shape[0], z.device)
         h = self.conv3(a, D + "conv_in", causal, want_stats=True)
         if self.sd3:
             h = self.resblock(h, D + "mid_block.resnets.0", causal)

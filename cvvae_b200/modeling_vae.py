@@ -68,7 +68,14 @@ class DiagonalGaussianDistribution:
             self.var = self.std = torch.zeros_like(self.mean)
 
     def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        eps = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
+        # diffusers.utils.randn_tensor semantics: a CPU generator draws on the CPU and the noise is moved (pipelines
+        # commonly pass CPU generators for reproducibility across devices); otherwise draw on the tensor's device
+        dev = self.parameters.device
+        gdev = generator.device if generator is not None else dev
+        if gdev.type != dev.type:
+            eps = torch.randn(self.mean.shape, generator=generator, device=gdev, dtype=self.parameters.dtype).to(dev)
+        else:
+            eps = torch.randn(self.mean.shape, generator=generator, device=dev, dtype=self.parameters.dtype)
         return self.mean + self.std * eps
 
     def mode(self) -> torch.Tensor:
@@ -212,8 +219,11 @@ class _CVVAEBase(nn.Module):
     # ---- engine ---------------------------------------------------------------
     def _engine(self) -> Engine:
         p0 = next(self.parameters())
-        key = (p0.device, p0.dtype)
+        # parameter versions: in-place updates after the first call (param.data.copy_, weight merging, optimiser steps)
+        # must re-pack the weights, as the reference modules would simply see the new values
+        key = (p0.device, p0.dtype, sum(p._version for p in self.parameters()))
         if self._engine_cache is None or self._engine_cache[0] != key:
+            self._graph_cache = {}
             if self._ops_factory is not None:
                 ops = self._ops_factory()
             else:
@@ -248,6 +258,9 @@ class _CVVAEBase(nn.Module):
 
     def _run_net(self, which: str, x: torch.Tensor) -> torch.Tensor:
         self._check_input(x)
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):   # kernels, streams and graph capture belong to the model's device
+                return self._run_net(which, x)
         eng = self._engine()
         if (not self._graphs_enabled or self._ops_factory is not None or getattr(eng.ops, "profile", None) is not None
                 or torch.cuda.is_current_stream_capturing()):
@@ -308,9 +321,9 @@ class _CVVAEBase(nn.Module):
     def blend_v(self, a, b, overlap_size):
         return self._blend_v(a, b, overlap_size)
 
-    def _spatial_tiled(self, x: torch.Tensor, fn, in_tile: Optional[int], out_tile: Optional[int]) -> torch.Tensor:
-        if in_tile is None:
-            return fn(x)
+    def _tile_rows(self, x: torch.Tensor, fn, in_tile: int, out_tile: int):
+        """Run `fn` over the spatial tiles of one temporal chunk and blend them in place, in the reference's order.
+        Returns (rows of blended tiles, stride of the kept window of every tile but the last of a row / column)."""
         ratio = self.tile_overlap_ratio
         in_stride = round(in_tile * (1 - ratio))
         out_overlap = round(out_tile * ratio)
@@ -345,8 +358,6 @@ class _CVVAEBase(nn.Module):
                     results[(g[0], g[1])] = out[n * B:(n + 1) * B]
             k += len(group)
         rows = [[results[(r, c)] for c in range(len(row))] for r, row in enumerate(windows)]
-        if len(rows) == 1 and len(rows[0]) == 1:
-            return rows[0][0]
         # blend against the already blended upper / left neighbours, in place (reference order)
         for i, cols in enumerate(rows):
             for j, tile in enumerate(cols):
@@ -354,17 +365,41 @@ class _CVVAEBase(nn.Module):
                     self._blend_v(rows[i - 1][j], tile, out_overlap)
                 if j > 0:
                     self._blend_h(cols[j - 1], tile, out_overlap)
-        out_rows = []
+        return rows, out_stride
+
+    def _assemble(self, rows, out_stride: int, dst: torch.Tensor, t_src0: int = 0) -> None:
+        """Copy the kept window of every blended tile into its place of the pre-allocated result `dst`
+        ([B, C, T, H, W]; frames `t_src0:` of the tiles) - one strided copy kernel per tile instead of the reference's
+        crop + cat over columns + cat over rows (+ cat over chunks)."""
+        ops = self._engine().ops
+        y0 = 0
         for i, cols in enumerate(rows):
-            cropped = []
+            x0 = 0
+            h = out_stride if i < len(rows) - 1 else cols[0].shape[3]
             for j, tile in enumerate(cols):
-                if i < len(rows) - 1:
-                    tile = tile[:, :, :, :out_stride, :]
-                if j < len(cols) - 1:
-                    tile = tile[:, :, :, :, :out_stride]
-                cropped.append(tile)
-            out_rows.append(torch.cat(cropped, dim=4))
-        return torch.cat(out_rows, dim=3)
+                w = out_stride if j < len(cols) - 1 else tile.shape[4]
+                src = tile[:, :, t_src0:, :h, :w]
+                ops.copy(src.permute(0, 2, 3, 4, 1), dst[:, :, :, y0:y0 + h, x0:x0 + w].permute(0, 2, 3, 4, 1))
+                x0 += w
+            y0 += h
+
+    @staticmethod
+    def _assembled_hw(rows, out_stride: int) -> Tuple[int, int]:
+        hh = out_stride * (len(rows) - 1) + rows[-1][0].shape[3]
+        ww = out_stride * (len(rows[0]) - 1) + rows[0][-1].shape[4]
+        return hh, ww
+
+    def _spatial_tiled(self, x: torch.Tensor, fn, in_tile: Optional[int], out_tile: Optional[int]) -> torch.Tensor:
+        if in_tile is None:
+            return fn(x)
+        rows, out_stride = self._tile_rows(x, fn, in_tile, out_tile)
+        if len(rows) == 1 and len(rows[0]) == 1:
+            return rows[0][0]
+        t0 = rows[0][0]
+        hh, ww = self._assembled_hw(rows, out_stride)
+        out = torch.empty((t0.shape[0], t0.shape[1], t0.shape[2], hh, ww), dtype=t0.dtype, device=t0.device)
+        self._assemble(rows, out_stride, out)
+        return out
 
     def spatial_tiled_encode(self, x):
         return self._spatial_tiled(x, self.encoder, self.pixel_tile_size, self.latent_tile_size)
@@ -379,25 +414,41 @@ class _CVVAEBase(nn.Module):
         n_rounds = 1 if n_rounds == 0 else n_rounds
         return [(n * stride, (n + 1) * stride + 1) for n in range(n_rounds)]
 
-    def tiled_encode(self, x):
-        if self.encode_n_frames_a_time is None:
-            return self.spatial_tiled_encode(x)
+    def _chunked(self, x: torch.Tensor, fn, stride: Optional[int], in_tile: Optional[int], out_tile: Optional[int],
+                 out_frames) -> torch.Tensor:
+        """Temporal chunk loop x spatial tile loop of the reference, every (chunk, tile) result written ONCE into the
+        pre-allocated output: chunk n > 0 drops its first output frame (modeling_vae.py:204-206, 290-292)."""
+        if stride is None:
+            return self._spatial_tiled(x, fn, in_tile, out_tile)
         assert x.dim() == 5
-        zs = []
-        for n, (a, b) in enumerate(self._chunks(x.shape[2], self.encode_n_frames_a_time)):
-            z = self.spatial_tiled_encode(x[:, :, a:b])
-            zs.append(z if n == 0 else z[:, :, 1:])
-        return zs[0] if len(zs) == 1 else torch.cat(zs, dim=2)
+        chunks = self._chunks(x.shape[2], stride)
+        if len(chunks) == 1:
+            return self._spatial_tiled(x[:, :, chunks[0][0]:chunks[0][1]], fn, in_tile, out_tile)
+        lens = [out_frames(min(b, x.shape[2]) - a) - (1 if n else 0) for n, (a, b) in enumerate(chunks)]
+        out, t = None, 0
+        for n, (a, b) in enumerate(chunks):
+            xc = x[:, :, a:b]
+            if in_tile is None:
+                r = fn(xc)
+                rows, ostride = [[r]], r.shape[3]
+            else:
+                rows, ostride = self._tile_rows(xc, fn, in_tile, out_tile)
+            t0 = rows[0][0]
+            if out is None:
+                hh, ww = self._assembled_hw(rows, ostride)
+                out = torch.empty((t0.shape[0], t0.shape[1], sum(lens), hh, ww), dtype=t0.dtype, device=t0.device)
+            assert t0.shape[2] - (1 if n else 0) == lens[n], (t0.shape, lens, n)
+            self._assemble(rows, ostride, out[:, :, t:t + lens[n]], 1 if n else 0)
+            t += lens[n]
+        return out
+
+    def tiled_encode(self, x):
+        return self._chunked(x, self.encoder, self.encode_n_frames_a_time, self.pixel_tile_size, self.latent_tile_size,
+                             self._engine().encoded_frames)
 
     def tiled_decode(self, z, **kwargs):
-        if self.decode_n_frames_a_time is None:
-            return self.spatial_tiled_decode(z, **kwargs)
-        assert z.dim() == 5
-        xs = []
-        for n, (a, b) in enumerate(self._chunks(z.shape[2], self.decode_n_frames_a_time)):
-            x = self.spatial_tiled_decode(z[:, :, a:b], **kwargs)
-            xs.append(x if n == 0 else x[:, :, 1:])
-        return xs[0] if len(xs) == 1 else torch.cat(xs, dim=2)
+        return self._chunked(z, self.decoder, self.decode_n_frames_a_time, self.latent_tile_size, self.pixel_tile_size,
+                             self._engine().decoded_frames)
 
     # ---- encode / decode: modeling_vae.py:212-228, 298-319 ---------------------------
     def _maybe_offload_hook(self):

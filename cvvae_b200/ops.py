@@ -41,6 +41,29 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _on_tensor_device(fn):
+    """Run a CudaOps method with the CUDA device of its first tensor argument current.
+
+    The C ABI launches on the current device (kernel attributes, SM count and the stream handle are per device), so
+    a model living on cuda:1 while cuda:0 is current - single-process multi-GPU, diffusers device placement - must
+    switch for the duration of the call, exactly as a PyTorch operator would."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                dev = a.device
+                break
+        if dev is None or dev.type != "cuda" or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 class CudaOps:
     """The production operator set: every method is one (or two) hand-written sm_100a kernels."""
 
@@ -78,6 +101,7 @@ class CudaOps:
         return p, p[:, :, 1:-1, 1:-1, :]
 
     # ------------------------------------------------------------------ convolution / GEMM
+    @_on_tensor_device
     def pack_weight(self, w: torch.Tensor) -> torch.Tensor:
         """[Cout, Cin, *k] (PyTorch) -> [taps, Cout, Cin] in the same 16-bit dtype."""
         w = w.contiguous()
@@ -90,19 +114,25 @@ class CudaOps:
                 "cvvae_pack_conv_weight")
         return out
 
+    @_on_tensor_device
     def conv(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, kernel=(1, 1, 1),
              stride=(1, 1, 1), offset=(0, 0, 0), pad_t=L.PAD_ZERO, pad_hw=L.PAD_ZERO, up_time=1,
              residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
              out_f32: bool = False, bias_along_m: bool = False, w_ld: int = 0, cout: Optional[int] = None,
              force: Optional[str] = None, ref_taps: Optional[int] = None, gn_stats: Optional[torch.Tensor] = None,
-             gn_groups: int = 32) -> torch.Tensor:
-        """y = alpha * conv(x, w) + bias + residual.  ``w`` is packed [taps, Cout, Cin(ld)]."""
+             gn_groups: int = 32, w_per_batch: bool = False, x_shared: bool = False) -> torch.Tensor:
+        """y = alpha * conv(x, w) + bias + residual.  ``w`` is packed [taps, Cout, Cin(ld)].
+
+        Batched GEMM (attention): ``w_per_batch`` - w is [B, Cout, Cin(ld)], one matrix per batch item of y;
+        ``x_shared`` - x has batch 1 and is the left operand of every batch item."""
         B, T, H, W, Ci = x.shape
+        if x_shared:
+            B = out.shape[0]
         kt, kh, kw = kernel
         st, sh, sw = stride
         ot, oh, ow = offset
         Co = cout if cout is not None else w.shape[1]
-        assert w.shape[0] == kt * kh * kw, (w.shape, kernel)
+        assert w.shape[0] == (out.shape[0] if w_per_batch else kt * kh * kw), (w.shape, kernel)
         if out is None:
             # PyTorch conv arithmetic with the padding implied by the offsets: out = floor((in + pad - k)/s) + 1,
             # where the engine always passes offsets so that the reference's output extents result.
@@ -121,7 +151,8 @@ class CudaOps:
         d.pad_t, d.pad_hw = pad_t, pad_hw
         d.up_time = up_time
         d.dtype = dtype_code(x.dtype)
-        d.flags = (L.CONV_BIAS_ALONG_M if bias_along_m else 0) | (L.CONV_OUT_F32 if out_f32 else 0)
+        d.flags = ((L.CONV_BIAS_ALONG_M if bias_along_m else 0) | (L.CONV_OUT_F32 if out_f32 else 0) |
+                   (L.CONV_W_PER_BATCH if w_per_batch else 0) | (L.CONV_X_SHARED if x_shared else 0))
         d.alpha = alpha
         if gn_stats is not None:  # fp64 [B, groups, 2], zeroed by the caller; the epilogue accumulates into it
             assert gn_stats.dtype == torch.int64 and gn_stats.is_contiguous()
@@ -151,6 +182,7 @@ class CudaOps:
         self.profile["events"][path].append((s_ev, e_ev))
         return out
 
+    @_on_tensor_device
     def conv_stacked(self, x: torch.Tensor, w_stk: torch.Tensor, bias: Optional[torch.Tensor], *, kt: int, cout: int,
                      offset=(0, -1, -1), pad_t=L.PAD_ZERO, pad_hw=L.PAD_ZERO, out: torch.Tensor = None) -> torch.Tensor:
         """(KT x) 3 x 3 stride-1 convolution with Cout <= 4 through the tap-stacked kernel; w_stk is [KT, 80, Cin]."""
@@ -189,6 +221,7 @@ class CudaOps:
         """Zeroed int64 fixed-point [B, groups, 2] accumulator (sum * 2^20, sum^2 * 2^18) for conv-epilogue statistics."""
         return torch.zeros((B, groups, 2), dtype=torch.int64, device=device)
 
+    @_on_tensor_device
     def groupnorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *,
                   per_frame: bool = False, silu: bool = True, out: Optional[torch.Tensor] = None,
                   stats: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -210,6 +243,7 @@ class CudaOps:
                 "cvvae_groupnorm_apply")
         return out
 
+    @_on_tensor_device
     def layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
         out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
         xs, ys = _t5(x), _t5(out)
@@ -218,6 +252,7 @@ class CudaOps:
         return out
 
     # ------------------------------------------------------------------ attention helpers
+    @_on_tensor_device
     def softmax_rows(self, s: torch.Tensor, cols: int, out: torch.Tensor) -> torch.Tensor:
         """s: fp32 [rows, ld_s]; out: 16-bit [rows, ld_p]; softmax over the first `cols` of each row."""
         assert s.dtype == torch.float32 and s.dim() == 2 and out.dim() == 2 and s.stride(1) == 1 and out.stride(1) == 1
@@ -225,6 +260,7 @@ class CudaOps:
                                             dtype_code(out.dtype), _stream(s)), "cvvae_softmax_rows")
         return out
 
+    @_on_tensor_device
     def attn_temporal(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
         out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
         a, b, c, o = _t5(q), _t5(k), _t5(v), _t5(out)
@@ -233,24 +269,18 @@ class CudaOps:
         return out
 
     # ------------------------------------------------------------------ data movement
-    def upsample2x(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        B, T, H, W, Cc = x.shape
-        if out is None:
-            out = torch.empty((B, T, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
-        xs, ys = _t5(x), _t5(out)
-        L.check(self.lib.cvvae_upsample_nearest2x(C.byref(xs), C.byref(ys), dtype_code(x.dtype), _stream(x)),
-                "cvvae_upsample_nearest2x")
-        return out
-
+    @_on_tensor_device
     def replicate_border(self, xpad: torch.Tensor) -> None:
         xs = _t5(xpad)
         L.check(self.lib.cvvae_replicate_border(C.byref(xs), dtype_code(xpad.dtype), _stream(xpad)), "cvvae_replicate_border")
 
+    @_on_tensor_device
     def copy(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         xs, ys = _t5(x), _t5(out)
         L.check(self.lib.cvvae_copy5(C.byref(xs), C.byref(ys), dtype_code(x.dtype), _stream(x)), "cvvae_copy5")
         return out
 
+    @_on_tensor_device
     def blend(self, a: torch.Tensor, b: torch.Tensor, overlap: int, axis: int) -> torch.Tensor:
         """In place on b (logical [B,T,H,W,C] views): axis 0 = width (blend_h), 1 = height (blend_v)."""
         xs, ys = _t5(a), _t5(b)

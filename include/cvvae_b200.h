@@ -39,7 +39,11 @@ enum {
 enum {
   CVVAE_CONV_BIAS_ALONG_M = 1, /* bias indexed by flattened output position instead of channel */
   CVVAE_CONV_FORCE_DIRECT = 2, /* debugging: route cvvae_conv3d() to the CUDA-core kernel       */
-  CVVAE_CONV_OUT_F32 = 4       /* y holds fp32 (strides in fp32 elements); no residual, up_time 1  */
+  CVVAE_CONV_OUT_F32 = 4,      /* y holds fp32 (strides in fp32 elements); no residual, up_time 1  */
+  /* Batched GEMM over the B axis (the per-frame attention products, models/vae_models.py:446-461,500-528): */
+  CVVAE_CONV_W_PER_BATCH = 8,  /* `w` holds one [Cout][Cin(ld)] matrix PER batch item ([y.B][Cout][w_ld], contiguous);
+                                  1x1x1 flat problems only.  A CVVAE_CONV_BIAS_ALONG_M bias is then [T*H*W], shared  */
+  CVVAE_CONV_X_SHARED = 16     /* x.B == 1: the same left operand for every batch item of y                       */
 };
 
 /* One strided channels-last 5-D tensor view. */
@@ -138,9 +142,6 @@ int cvvae_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int6
  * for every (b,h,w): tokens = the T frames, one head of dim C.  q,k,v,o are [B,T,H,W,C] views. */
 int cvvae_attn_temporal(const cvvae_tensor5* q, const cvvae_tensor5* k, const cvvae_tensor5* v,
                         const cvvae_tensor5* o, int32_t dtype, void* stream);
-
-/* Nearest-neighbour x(1,2,2) upsample (F.interpolate in Upsample3D, models/vae_models.py:218-220). */
-int cvvae_upsample_nearest2x(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream);
 
 /* Replicate the outermost valid row/column of the interior [1,H-1)x[1,W-1) into the 1-pixel frame of
  * a spatially pre-padded buffer (replicate padding of the sd3 convs, vae_blocks3d_sd3.py:87-98). */

@@ -46,9 +46,16 @@ class FakeOps:
 
     def conv(self, x, w, bias, *, kernel=(1, 1, 1), stride=(1, 1, 1), offset=(0, 0, 0), pad_t=PAD_ZERO, pad_hw=PAD_ZERO,
              up_time=1, residual=None, alpha=1.0, out=None, out_f32=False, bias_along_m=False, w_ld=0, cout=None,
-             force=None, ref_taps=None, gn_stats=None, gn_groups=32):
+             force=None, ref_taps=None, gn_stats=None, gn_groups=32, w_per_batch=False, x_shared=False):
         self.launches += 1
         assert out is not None
+        if w_per_batch or x_shared:
+            # batched GEMM: one (x_b, w_b) product per batch item of `out`; a row bias is shared by the items
+            for bi in range(out.shape[0]):
+                self.conv(x[0:1] if x_shared else x[bi:bi + 1], w[bi:bi + 1] if w_per_batch else w, bias, kernel=kernel,
+                          alpha=alpha, out=out[bi:bi + 1], out_f32=out_f32, bias_along_m=bias_along_m, w_ld=w_ld, cout=cout)
+            self.launches -= out.shape[0]
+            return out
         kt, kh, kw = kernel
         B, T, H, W, Ci = x.shape
         Co = cout if cout is not None else w.shape[1]
@@ -164,14 +171,6 @@ class FakeOps:
         return o.to(q.dtype).contiguous()
 
     # ---- data movement
-    def upsample2x(self, x, out=None):
-        self.launches += 1
-        y = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
-        if out is None:
-            return y.contiguous()
-        out.copy_(y)
-        return out
-
     def replicate_border(self, xpad):
         self.launches += 1
         H, W = xpad.shape[2], xpad.shape[3]

@@ -246,8 +246,6 @@ def test_layernorm_softmax_temporal_attention():
 
 def test_data_movement_is_bit_exact():
     ops, fake = _ops(), FakeOps()
-    x = _rand((1, 3, 10, 12, 64), torch.float16, 40)
-    assert torch.equal(ops.upsample2x(x), fake.upsample2x(x))
     a = _rand((1, 8, 3, 20, 24), torch.float16, 41)  # NCDHW tiles as the wrapper holds them
     b1 = _rand((1, 8, 3, 20, 24), torch.float16, 42)
     b2 = b1.clone()
