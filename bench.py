@@ -1,24 +1,34 @@
 #!/usr/bin/env python
-"""bench.py - video VAE encode+decode frames/sec at 17x576x1024 (BASELINE.json metric), one JSON line.
+"""bench.py - video VAE encode+decode frames/sec (BASELINE.json metric), one JSON line.
 
-    python bench.py --gpus 1 --steps K --warmup W          # this framework (CUDA engine through the C ABI)
+    python bench.py --gpus 1 --steps K --warmup W          # this framework (CUDA engine through the C ABI), config c2
+    python bench.py --config c3|c4|c5 ...                  # the other BASELINE.json configs through the same harness
     python bench.py --impl reference ...                   # the reference algorithm on the host CPU cores
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" = encode(x).latent_dist.mode() -> decode(z).sample of one synthetic fp16 clip through the public
-CVVAEModel API, wrapper tiling/chunking on (17x576x1024 = 1 chunk x 2 tiles of 576x576).
-  value      frames/s, clip resident in HBM when the timed region starts
-  e2e        same, host (pinned) clip -> H2D -> encode/decode -> D2H of the reconstruction, per step
-  roofline   tensor bound of the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of its
-             launches / their CUDA-event time, against MEASURED_PEAKS.json (sustained bf16 cuBLAS TF/s)
-  cpu_baseline  the oracle (CPU restatement of the reference algorithm, fp32) on the host cores, on a
-             bounded sample, scaled to the workload by computed pixel count
-N>1: the clip grows to 1+16N frames, sharded on the frame axis (one 17-frame chunk per rank, weak scaling),
-one NCCL halo exchange per codec direction (cvvae_b200/parallel.py).
+A "step" = encode(x).latent_dist.mode() -> decode(z).sample of one synthetic clip (or clip batch) through the public
+model API, wrapper tiling/chunking on.  Configs (BASELINE.json `configs[1..4]`):
+  c2  17x3x576x1024 fp16, SD2.1 model (1 chunk x 2 tiles of 576x576); N GPUs: clip of 1+16N frames, frame-sharded,
+      one chunk per rank (weak scaling), one NCCL halo frame per codec direction
+  c3  33x3x512x512 bf16, SD3 model (2 chunks, un-tiled); N GPUs: 1+32N frames, two chunks per rank (weak)
+  c4  129x3x720x1280 fp16 (8 chunks x 6 ragged tiles), the 8 chunks split over N ranks with the halo exchange (strong)
+  c5  batch-32 of 17x3x256x256 fp16, 32/N clips per rank, no communication (strong)
+Keys:
+  value      frames/s, inputs resident in HBM when the timed region starts
+  e2e        same through host buffers: pinned host clip -> H2D -> encode/decode -> D2H of the reconstruction, per step
+  roofline   tensor bound of the dominant kernels (tcgen05 implicit-GEMM conv): algorithmic FLOPs of their launches /
+             their CUDA-event time in the timed region, against MEASURED_PEAKS.json (sustained bf16 cuBLAS TF/s)
+  cpu_baseline        the oracle (CPU restatement of the reference algorithm, fp32) on the host cores, on a bounded
+             sample, scaled to the workload by network-input pixel count            (N = 1, rank 0)
+  torch_cuda_baseline the reference ALGORITHM in the bench dtype on torch-CUDA library kernels (cuDNN / SDPA), eager,
+             wrapper tiling on, cudnn.benchmark False and True - the north_star's ">= 4x" denominator (N = 1, c2/c3)
+  parity_sharded      N > 1: rank 0 also runs the un-sharded clip and the gathered sharded result must be
+             bit-identical (moments and reconstruction); the line carries the verdict
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -33,7 +43,17 @@ import torch  # noqa: E402
 
 METRIC = "video VAE encode+decode frames/sec at 17x576x1024"
 UNIT = "frames/s"
-SAMPLE_SHAPE = (1, 3, 17, 192, 192)  # bounded CPU sample (~14 s on the 16 usable cores of a 1-GPU box)
+
+CONFIGS = {
+    "c2": dict(variant="sd21", dtype="fp16", frames=17, height=576, width=1024, batch=1, scaling="weak", chunks_per_rank=1,
+               metric=METRIC),
+    "c3": dict(variant="sd3", dtype="bf16", frames=33, height=512, width=512, batch=1, scaling="weak", chunks_per_rank=2,
+               metric="video VAE encode+decode frames/sec at 33x512x512 (SD3 model, bf16)"),
+    "c4": dict(variant="sd21", dtype="fp16", frames=129, height=720, width=1280, batch=1, scaling="strong",
+               metric="video VAE encode+decode frames/sec at 129x720x1280"),
+    "c5": dict(variant="sd21", dtype="fp16", frames=17, height=256, width=256, batch=32, scaling="strong",
+               metric="video VAE encode+decode frames/sec, batch-32 of 17x256x256"),
+}
 
 
 def parse():
@@ -42,12 +62,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-cuda"])
-    ap.add_argument("--frames", type=int, default=17)
-    ap.add_argument("--height", type=int, default=576)
-    ap.add_argument("--width", type=int, default=1024)
-    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--dtype", default=None, choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded == un-sharded check at N > 1")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    for k in ("frames", "height", "width", "dtype"):
+        if getattr(args, k) is not None:
+            cfg[k] = getattr(args, k)
+    args.cfg = cfg
+    args.frames, args.height, args.width, args.dtype = cfg["frames"], cfg["height"], cfg["width"], cfg["dtype"]
+    return args
 
 
 def peaks():
@@ -57,6 +87,16 @@ def peaks():
             d = json.load(f)
         return float(d.get("bf16_tflops_sustained", 1400.0)), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
     return 1400.0, "fallback 1.4 PFLOP/s sustained (of fallback)"
+
+
+def source_hash():
+    """sha256 over the CUDA sources + the C header: identifies the kernels a committed ncu capture belongs to."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "cvvae_b200", "csrc")
+    for f in sorted(os.listdir(d)) + ["../../include/cvvae_b200.h"]:
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -131,75 +171,88 @@ def usable_cores():
     return n
 
 
-def sample_shape(steps):
-    """Bounded CPU sample per step, shrunk when many steps are asked for so that the arm ends within a few minutes."""
-    side = 192 if steps <= 6 else (128 if steps <= 24 else 96)
+def sample_shape(n_runs):
+    """Bounded CPU sample per step, shrunk when many runs are asked for so that the arm ends within a few minutes."""
+    side = 192 if n_runs <= 6 else (128 if n_runs <= 26 else 96)
     return (1, 3, 17, side, side)
 
 
-def cpu_sample(steps=1, shape=None):
+def oracle_cfg(cfg, **wrap):
+    from oracle import cvvae_oracle as O
+    if cfg["variant"] == "sd21":
+        return O.VAEConfig(variant="sd21", **wrap)
+    return O.VAEConfig(variant="sd3", z_channels=16, **wrap)
+
+
+def cpu_sample(cfg, steps=1, shape=None, warmup=0):
     """Reference algorithm (oracle port, fp32) on the host cores on a bounded sample."""
     from oracle import cvvae_oracle as O  # the one place bench.py executes oracle/: the CPU baseline
     cores = usable_cores()
     torch.set_num_threads(cores)
-    wrap = dict(tile_spatial_size=None, en_de_n_frames_a_time=None)
-    cfg = O.VAEConfig(variant="sd21", **wrap)
-    sd = O.make_state_dict(cfg, 1234)
-    x = O.synthetic_video(shape or SAMPLE_SHAPE, 0)
+    ocfg = oracle_cfg(cfg, tile_spatial_size=None, en_de_n_frames_a_time=None)
+    sd = O.make_state_dict(ocfg, 1234)
+    x = O.synthetic_video(shape, 0)
     with torch.no_grad():
-        O.decode(O.encode(O.synthetic_video((1, 3, 1, 32, 32), 0), sd, cfg).mode(), sd, cfg)  # page in oneDNN
+        O.decode(O.encode(O.synthetic_video((1, 3, 1, 32, 32), 0), sd, ocfg).mode(), sd, ocfg)  # page in oneDNN
+        for _ in range(warmup):
+            O.decode(O.encode(x, sd, ocfg).mode(), sd, ocfg)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.decode(O.encode(x, sd, cfg).mode(), sd, cfg)
+            O.decode(O.encode(x, sd, ocfg).mode(), sd, ocfg)
         dt = (time.perf_counter() - t0) / steps
     return dt, cores
 
 
-def workload_pixels(frames, height, width):
-    """Pixels the wrapper actually pushes through the networks (tile overlap included)."""
-    def tiles(n, tile=576, stride=448):
-        out, i = [], 0
-        while True:
-            out.append(min(tile, n - i))
-            if i + tile >= n:
-                break
-            i += stride
-        return out
-    return frames * sum(tiles(height)) * sum(tiles(width))
+def tiles_1d(n, tile=576, stride=448):
+    out, i = [], 0
+    while True:
+        out.append(min(tile, n - i))
+        if i + tile >= n:
+            break
+        i += stride
+    return out
 
 
-def cpu_baseline_entry(args, steps=1):
-    shp = sample_shape(steps)
-    dt, cores = cpu_sample(steps, shp)
-    ratio = workload_pixels(args.frames, args.height, args.width) / (shp[2] * shp[3] * shp[4])
-    fps = args.frames / (dt * ratio)
+def workload_pixels(frames, height, width, batch=1, chunk=16):
+    """Pixels the wrapper actually pushes through the networks (tile overlap and the re-encoded chunk frames included)."""
+    n_chunks = max(1, -(-(frames - 1) // chunk))
+    net_frames = sum(min(chunk * (n + 1) + 1, frames) - chunk * n for n in range(n_chunks))
+    return batch * net_frames * sum(tiles_1d(height)) * sum(tiles_1d(width))
+
+
+def cpu_baseline_entry(args, steps=1, warmup=0):
+    cfg = args.cfg
+    shp = sample_shape(steps + warmup)
+    dt, cores = cpu_sample(cfg, steps, shp, warmup)
+    ratio = workload_pixels(args.frames, args.height, args.width, cfg["batch"]) / (shp[2] * shp[3] * shp[4])
+    fps = cfg["batch"] * args.frames / (dt * ratio)
     return {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle fp32 encode+decode of one {shp[2]}x{shp[3]}x{shp[4]} clip "
+            "sample": f"oracle fp32 ({cfg['variant']} nets) encode+decode of one {shp[2]}x{shp[3]}x{shp[4]} clip "
                       f"({dt:.2f} s), scaled x{ratio:.1f} by network-input pixel count to "
-                      f"{args.frames}x{args.height}x{args.width} (tile overlap of the 576/448 tiling included)"}, dt
+                      f"{cfg['batch']}x{args.frames}x{args.height}x{args.width} (tile overlap of the 576/448 tiling and the "
+                      f"re-encoded chunk-boundary frames included)"}, dt
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps = max(1, args.steps)
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(1)
-    entry, dt = cpu_baseline_entry(args, steps)
-    line = {"impl": "reference", "metric": METRIC, "value": entry["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.frames}x3x{args.height}x{args.width} encode+decode, bounded CPU sample per step"},
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    entry, dt = cpu_baseline_entry(args, steps, warm)
+    line = {"impl": "reference", "metric": args.cfg["metric"], "value": entry["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": args.cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.cfg['batch']}x{args.frames}x3x{args.height}x{args.width} encode+decode ({args.config}), "
+                                   f"bounded CPU sample per step"},
             "cpu_baseline": entry,
             "e2e": {"value": entry["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arms
-def build_model(dtype):
-    from cvvae_b200 import CVVAEModel
+def build_model(cfg, dtype):
+    from cvvae_b200 import CVVAEModel, CVVAESD3Model
     torch.manual_seed(1234)
-    m = CVVAEModel()  # reference defaults: 4-ch latent, tile 576, chunks of 16(+1) frames
+    m = CVVAEModel() if cfg["variant"] == "sd21" else CVVAESD3Model()   # reference defaults: tile 576, chunks of 16(+1)
     g = torch.Generator().manual_seed(4321)
     for k, p in m.named_parameters():  # non-trivial affine/bias so nothing is skipped or degenerate
         if p.dim() == 1:
@@ -208,15 +261,18 @@ def build_model(dtype):
 
 
 class TorchCudaReference:
-    """The reference algorithm on torch-CUDA library kernels (cuDNN etc.) - informational arm only
-    (`--impl torch-cuda`): the north_star's '>= 4x the reference's own torch-cuda' denominator."""
+    """The reference algorithm on torch-CUDA library kernels (cuDNN etc.): the north_star's '>= 4x the reference's own
+    torch-cuda' denominator.  The reference is Python and /root/reference does not exist on the GPU box, so this runs its
+    pinned restatement (oracle/, checked against the reference's own outputs in tests/test_oracle_golden.py) with the
+    same state dict as the engine; kind = "port"."""
 
-    def __init__(self, dtype):
+    def __init__(self, cfg, state_dict):
         from oracle import cvvae_oracle as O
         self.O = O
-        self.cfg = O.VAEConfig(variant="sd21")
-        m = build_model(dtype)
-        self.sd = {k: v for k, v in m.state_dict().items()}
+        self.cfg = oracle_cfg(cfg)
+        self.sd = state_dict
+        self.encode_n_frames_a_time = 16
+        self.decode_n_frames_a_time = 4
 
     def tiled_encode(self, x):
         return self.O.tiled_encode(x, self.sd, self.cfg)
@@ -224,12 +280,38 @@ class TorchCudaReference:
     def tiled_decode(self, z):
         return self.O.tiled_decode(z, self.sd, self.cfg)
 
-    encode_n_frames_a_time = 16
-    decode_n_frames_a_time = 4
+
+def time_torch_cuda(ref, x, zc, warmup=3, reps=10):
+    """frames/s of the torch-CUDA reference arm: CUDA events, `warmup` untimed passes, median of `reps`."""
+    def step():
+        with torch.no_grad():
+            return ref.tiled_decode(ref.tiled_encode(x)[:, :zc])
+    out = {}
+    frames = x.shape[0] * x.shape[2]
+    for bench_flag in (False, True):
+        torch.backends.cudnn.benchmark = bench_flag
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ts.sort()
+        out["cudnn_benchmark_" + ("true" if bench_flag else "false")] = {"frames_per_s": frames / (ts[len(ts) // 2] * 1e-3),
+                                                                          "ms_per_step_median": ts[len(ts) // 2]}
+    torch.backends.cudnn.benchmark = False
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
     args = parse()
+    cfg = args.cfg
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -243,36 +325,71 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
-    zc = 4
+    zc = 4 if cfg["variant"] == "sd21" else 16
 
-    if args.impl == "ours":
-        import __graft_entry__ as ge
-        if rank == 0:
-            ge.build()
-        if world > 1:
-            dist.barrier()
-        model = build_model(dtype)
-        ops = model._engine().ops
-    else:
-        model = TorchCudaReference(dtype)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    model = build_model(cfg, dtype)
+    ops = model._engine().ops
+    if args.impl == "torch-cuda":
+        net = TorchCudaReference(cfg, dict(model.state_dict()))
         ops = None
+    else:
+        net = model
 
-    from cvvae_b200.parallel import FrameShardedVAE
-    sharded = FrameShardedVAE(model) if world > 1 else None
+    # ---- this rank's share of the work
+    from cvvae_b200.parallel import FrameShardedVAE, chunk_ranges, frame_range
+    stride = 16
+    F, B = args.frames, cfg["batch"]
+    sharded, total_chunks = None, None
+    if cfg["scaling"] == "weak":            # c2 / c3: (F-1)/16 chunks per rank, clip of 1 + (F-1) N frames
+        cpr = (F - 1) // stride
+        total_chunks = cpr * world
+        total_frames = 1 + (F - 1) * world
+        ranges = [(r * cpr, (r + 1) * cpr) for r in range(world)]
+        b_local = B
+    elif B == 1:                            # c4: fixed clip, its chunks split over the ranks
+        total_chunks = (F - 1) // stride
+        total_frames = F
+        ranges = chunk_ranges(total_chunks, world)
+        b_local = B
+    else:                                   # c5: fixed batch of clips, split over the ranks
+        assert B % world == 0, "batch must divide over the ranks"
+        total_frames = F
+        ranges = [(0, (F - 1) // stride)] * world
+        b_local = B // world
+    if world > 1 and B == 1:
+        assert args.impl == "ours"
+        sharded = FrameShardedVAE(model)
+    c0, c1 = ranges[rank]
+    f0, f1 = (frame_range(c0, c1, stride) if (sharded is not None and c1 > c0) else (0, (F if sharded is None else 0)))
 
-    # this rank's shard of the clip: rank 0 holds frames 0..16, rank r frames 16r+1..16r+16
-    n_local = args.frames if rank == 0 else args.frames - 1
-    g = torch.Generator().manual_seed(rank)
-    x_host = (torch.rand((1, 3, n_local, args.height, args.width), generator=g) * 2 - 1).to(dtype).pin_memory()
+    def gen_chunk_frames(a, b, seed_base=0):
+        """Frames [a, b) of the (virtual) whole clip: one seeded block per 16-frame chunk so that any rank can rebuild any part."""
+        parts = []
+        t = a
+        while t < b:
+            c = 0 if t == 0 else (t - 1) // stride
+            lo, hi = frame_range(c, c + 1, stride)
+            g = torch.Generator().manual_seed(1000 + seed_base + c)
+            blk = (torch.rand((b_local, 3, hi - lo, args.height, args.width), generator=g) * 2 - 1).to(dtype)
+            parts.append(blk[:, :, t - lo:min(b, hi) - lo])
+            t = min(b, hi)
+        return torch.cat(parts, dim=2) if len(parts) > 1 else parts[0]
+
+    x_host = gen_chunk_frames(f0, f1, seed_base=(rank * 100 if sharded is None and world > 1 else 0)).pin_memory()
     x_dev = x_host.cuda()
 
     def step(x):
         with torch.no_grad():
             if sharded is not None:
-                z = sharded.encode_local(x)[:, :zc].contiguous()
-                return sharded.decode_local(z)
-            z = model.tiled_encode(x)[:, :zc]
-            return model.tiled_decode(z)
+                z = sharded.encode_local(x, total_chunks)[:, :zc].contiguous()
+                return sharded.decode_local(z, total_chunks)
+            z = net.tiled_encode(x)[:, :zc]
+            return net.tiled_decode(z)
 
     def sync():
         torch.cuda.synchronize()
@@ -293,6 +410,33 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # ---- N > 1: sharded result == un-sharded result of the same engine, checked on rank 0 before anything is timed
+    parity = None
+    if sharded is not None and not args.no_parity:
+        with torch.no_grad():
+            mom_l = sharded.encode_local(x_dev, total_chunks)
+            rec_l = sharded.decode_local(mom_l[:, :zc].contiguous(), total_chunks)
+            lens_p = [frame_range(a, b, stride)[1] - frame_range(a, b, stride)[0] if b > a else 0 for a, b in ranges]
+            lens_l = [frame_range(a, b, stride // 4)[1] - frame_range(a, b, stride // 4)[0] if b > a else 0 for a, b in ranges]
+            mom_g = sharded.gather_frames(mom_l, lens_l)
+            rec_g = sharded.gather_frames(rec_l, lens_p)
+            if rank == 0:
+                x_full = gen_chunk_frames(0, total_frames).cuda()
+                mom_f = model.tiled_encode(x_full)
+                rec_f = model.tiled_decode(mom_f[:, :zc].contiguous())
+                parity = bool(torch.equal(mom_f, mom_g) and torch.equal(rec_f, rec_g))
+                del x_full, mom_f, rec_f
+            del mom_g, rec_g, mom_l, rec_l
+        torch.cuda.empty_cache()
+        flag = torch.tensor([1 if (parity or rank != 0) else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0:
+            if rank == 0:
+                print(json.dumps({"metric": cfg["metric"], "n_gpus": world, "parity_sharded": False,
+                                  "error": "sharded encode/decode differs from the un-sharded run of the same engine"}))
+            dist.destroy_process_group()
+            sys.exit(1)
+
     for _ in range(max(args.warmup, 3)):
         out = step(x_dev)
     sync()
@@ -307,8 +451,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = (ops.launch_count() - launches0) if ops else 0
     ms_step = ms_total / args.steps
-    total_frames = args.frames + (world - 1) * (args.frames - 1)
-    value = total_frames / (ms_step * 1e-3)
+    job_frames = B * total_frames
+    value = job_frames / (ms_step * 1e-3)
 
     # ---- end-to-end: pinned host clip -> H2D -> encode/decode -> D2H of the reconstruction, every step
     rec_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
@@ -323,9 +467,12 @@ def main():
     e2e_step()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
-    e2e = {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT, "cuda_graphs": args.impl == "ours",
+    e2e = {"value": job_frames / (ms_e2e * 1e-3), "unit": UNIT, "cuda_graphs": args.impl == "ours",
            "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
            "d2h_bytes_per_step": rec_host.numel() * rec_host.element_size()}
+    if args.impl == "ours":
+        model.enable_cuda_graphs(False)
+    peak_hbm = round(torch.cuda.max_memory_allocated() / 1e9, 2)  # activations + weights + graph pools, this rank
 
     if rank != 0:
         if world > 1:
@@ -337,15 +484,19 @@ def main():
     if prof and prof["conv_tc"]["ms"] > 0:
         tc = prof["conv_tc"]
         achieved = tc["flops"] / (tc["ms"] * 1e-3) / 1e12
-        traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):  # ncu dram bytes (read + write) per conv_tc launch, from the committed capture of this command
+        traffic, traffic_src, traffic_stale = None, None, None
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tp) and args.config == "c2":
+            # ncu dram bytes (read + write) per conv launch of this command, from the committed capture; stamped with the
+            # hash of the CUDA sources it was captured from - a mismatch means the kernels changed since (stale)
             with open(tp) as f:
                 tj = json.load(f)
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of the timed region)",
+            traffic_stale = tj.get("source_hash") != source_hash()
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc_psw_kernel / conv_stk_kernel (tcgen05 implicit-GEMM conv, all "
+                                             "launches of the timed region)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src,
+                "traffic_source": traffic_src, "traffic_stale": traffic_stale,
                 "algorithmic_bytes_per_launch": tc["bytes"] / max(tc["launches"], 1),
                 "peak_source": peak_src, "algorithmic_tflop_per_step": tc["flops"] / args.steps / 1e12,
                 "kernel_ms_per_step": tc["ms"] / args.steps, "launches_per_step": tc["launches"] / args.steps,
@@ -355,26 +506,37 @@ def main():
                 "reference_dense_tflop_per_step": tc["ref_flops"] / args.steps / 1e12,
                 "achieved_vs_reference_count": tc["ref_flops"] / (tc["ms"] * 1e-3) / 1e12,
                 "conv_direct_ms_per_step": prof["conv_direct"]["ms"] / args.steps}
-    def _n(n, tile=576, stride=448):
-        k, i = 1, 0
-        while i + tile < n:
-            i += stride
-            k += 1
-        return k
-    n_tiles = _n(args.height) * _n(args.width)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    n_tiles = len(tiles_1d(args.height)) * len(tiles_1d(args.width))
+    par = (f"frame-shard x{world}" if sharded is not None else (f"batch-shard x{world}" if world > 1 else "single GPU"))
+    line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"{total_frames}x3x{args.height}x{args.width} clip, encode(x).mode() -> decode(z), "
-                                   f"wrapper tiling 576/448 + 16-frame chunks; SD2.1-variant CVVAEModel, seeded random weights",
-                       "per_gpu": f"one {args.frames}-frame chunk = {n_tiles} spatial tiles (<= 576x576, stride 448)", "parallelism": f"frame-shard x{world}",
-                       "l2": "no explicit flush: every step streams >100 GB of activations (each up to 1.4 GB) through a 126 MB L2"},
-            "impl": args.impl, "gpu_launches": launches // args.steps if launches else 0, "clocks": clocks, "e2e": e2e}
-    line["peak_hbm_gb"] = round(torch.cuda.max_memory_allocated() / 1e9, 2)  # activations + weights + graph pools, this rank
+            "config": {"name": args.config,
+                       "workload": f"{B}x{total_frames}x3x{args.height}x{args.width} clip{'s' if B > 1 else ''}, encode(x).mode() -> "
+                                   f"decode(z), wrapper tiling 576/448 + 16-frame chunks; {cfg['variant'].upper()}-variant model, "
+                                   f"seeded random weights",
+                       "per_gpu": f"{b_local} x {c1 - c0} chunk(s) of <= 17 frames x {n_tiles} spatial tile(s) (<= 576x576, stride 448)",
+                       "parallelism": par,
+                       "l2": "no explicit flush: every step streams far more than the 126 MB L2 (activations up to 1.4 GB each)"},
+            "impl": args.impl, "gpu_launches": launches // args.steps if launches else 0, "clocks": clocks, "e2e": e2e,
+            "peak_hbm_gb": peak_hbm, "source_hash": source_hash()}
+    if parity is not None:
+        line["parity_sharded"] = parity
     if roof:
         line["roofline"] = roof
-    if args.impl == "ours" and not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_entry(args, 1)[0]
+    if args.impl == "ours" and world == 1:
+        if not args.no_torch_baseline and args.config in ("c2", "c3"):
+            ref = TorchCudaReference(cfg, dict(model.state_dict()))
+            tcb = time_torch_cuda(ref, x_dev, zc, warmup=3, reps=10)
+            tcb.update({"kind": "port", "unit": UNIT, "dtype": args.dtype,
+                        "what": "reference algorithm (oracle restatement pinned to the reference's outputs) on torch-CUDA library "
+                                "kernels, eager, wrapper tiling/chunking on, same state dict and input; CUDA events, 3 warm-ups, "
+                                "median of 10; the reference's own modules cannot travel to the GPU box (/root/reference absent)"})
+            tcb["speedup_value_vs_cudnn_benchmark_false"] = value / tcb["cudnn_benchmark_false"]["frames_per_s"]
+            tcb["speedup_value_vs_cudnn_benchmark_true"] = value / tcb["cudnn_benchmark_true"]["frames_per_s"]
+            line["torch_cuda_baseline"] = tcb
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_entry(args, 1)[0]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -61,7 +61,7 @@ _SIGNATURES = {
     "cvvae_last_error": (C.c_char_p, []),
     "cvvae_abi_version": (C.c_int, []),
     "cvvae_launch_count": (C.c_int64, []),
-    "cvvae_probe_umma_shift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "cvvae_probe_umma_shift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

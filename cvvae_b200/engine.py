@@ -136,6 +136,15 @@ class Engine:
                 T = 2 * T - 1
         return T
 
+    def encoded_hw(self, n: int) -> int:
+        """Latent extent of a pixel extent: one stride-2 3-tap conv per level but the last, pads (0,1) (sd21) / (1,1) (sd3)."""
+        for _ in range(len(self.cfg.widths) - 1):
+            n = (n + (2 if self.sd3 else 1) - 3) // 2 + 1
+        return n
+
+    def decoded_hw(self, n: int) -> int:
+        return n * 2 ** (len(self.cfg.widths) - 1)
+
     # ------------------------------------------------------------------ GroupNorm-sum accumulators
     _STATS_SLOTS = 96  # >= convolutions with fused statistics in one encoder / decoder pass (sd21 decoder: 49)
 

@@ -158,6 +158,7 @@ class _CVVAEBase(nn.Module):
         self._graph_cache = {}
         self._graph_pool = None
         self._graph_max = 8
+        self._tile_runner = None   # parallel.UnitShardedVAE installs its distributed tile loop here
         self.requires_grad_(False)
         self.eval()
 
@@ -237,6 +238,13 @@ class _CVVAEBase(nn.Module):
             packed = prepack_params(self.state_dict(), ops, p0.dtype)
             self._engine_cache = (key, Engine(self.net, packed, ops, p0.dtype))
         return self._engine_cache[1]
+
+    def invalidate_weights(self):
+        """Drop the pre-packed weights and captured graphs (call after writing parameters through `.data`, which the
+        version check in `_engine` cannot see)."""
+        self._engine_cache = None
+        self._graph_cache = {}
+        return self
 
     def enable_cuda_graphs(self, enabled: bool = True, max_cached: int = 8):
         """Replay each network call (one encoder / decoder pass over a tile batch) as a captured CUDA graph.
@@ -342,8 +350,23 @@ class _CVVAEBase(nn.Module):
             if i + in_tile >= x.shape[3]:
                 break
         flat = [(r, c, x[:, :, :, i:i + in_tile, j:j + in_tile]) for r, row in enumerate(windows) for c, (i, j) in enumerate(row)]
+        results = (self._tile_runner or self._run_tiles_local)(flat, fn)
+        rows = [[results[(r, c)] for c in range(len(row))] for r, row in enumerate(windows)]
+        # blend against the already blended upper / left neighbours, in place (reference order)
+        for i, cols in enumerate(rows):
+            for j, tile in enumerate(cols):
+                if i > 0:
+                    self._blend_v(rows[i - 1][j], tile, out_overlap)
+                if j > 0:
+                    self._blend_h(cols[j - 1], tile, out_overlap)
+        return rows, out_stride
+
+    def _run_tiles_local(self, flat, fn):
+        """flat = [(row, col, tile view)] -> {(row, col): network output}; equally shaped neighbours share a batch."""
         results = {}
-        B = x.shape[0]
+        if not flat:
+            return results
+        B = flat[0][2].shape[0]
         k = 0
         while k < len(flat):
             group = [flat[k]]
@@ -357,15 +380,7 @@ class _CVVAEBase(nn.Module):
                 for n, g in enumerate(group):
                     results[(g[0], g[1])] = out[n * B:(n + 1) * B]
             k += len(group)
-        rows = [[results[(r, c)] for c in range(len(row))] for r, row in enumerate(windows)]
-        # blend against the already blended upper / left neighbours, in place (reference order)
-        for i, cols in enumerate(rows):
-            for j, tile in enumerate(cols):
-                if i > 0:
-                    self._blend_v(rows[i - 1][j], tile, out_overlap)
-                if j > 0:
-                    self._blend_h(cols[j - 1], tile, out_overlap)
-        return rows, out_stride
+        return results
 
     def _assemble(self, rows, out_stride: int, dst: torch.Tensor, t_src0: int = 0) -> None:
         """Copy the kept window of every blended tile into its place of the pre-allocated result `dst`

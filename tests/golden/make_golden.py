@@ -52,6 +52,14 @@ CASES = [
          shape=(1, 3, 9, 104, 120)),
     dict(name="sd3_w128_plain", variant="sd3", ch=128, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None),
          shape=(1, 3, 5, 32, 32)),
+    # full-width models on inputs large enough for a non-trivial mid-block (attention over 8 x 8 = 64 tokens, 3 latent
+    # frames) and, tiled + chunked, for the whole wrapper (2 chunks x 2 x 2 ragged tiles of <= 64 px, blends both ways)
+    dict(name="sd21_w128_mid", variant="sd21", ch=128, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None),
+         shape=(1, 3, 9, 64, 64)),
+    dict(name="sd3_w128_mid", variant="sd3", ch=128, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None),
+         shape=(1, 3, 9, 64, 64)),
+    dict(name="sd21_w128_tiled", variant="sd21", ch=128, wrap=dict(tile_spatial_size=64, en_de_n_frames_a_time=4),
+         shape=(1, 3, 9, 96, 112)),
 ]
 WEIGHT_SEED = 1234
 INPUT_SEED = 0

@@ -97,3 +97,69 @@ def test_single_frame_time_tap_folding(variant):
     np.testing.assert_allclose(rec.numpy(), want_rec.numpy(), rtol=1e-4, atol=5e-5)
     folded = [k for k in m._engine().p if ".t1." in k and not k.endswith(".bias")]
     assert folded and all(m._engine().p[k].shape[0] in (4, 9) for k in folded)     # 2x2 phases / 3x3: no time taps left
+
+
+def test_diagonal_gaussian_distribution_contract():
+    """diffusers' DiagonalGaussianDistribution as the reference uses it (models/modeling_vae.py:223; training twin
+    lvdm/modules/distributions/distributions.py:24-73): chunk, logvar clamp to [-30, 20], std = exp(0.5 logvar),
+    sample(generator) = mean + std * randn (diffusers randn_tensor: drawn on the generator's device), mode = mean."""
+    from cvvae_b200.modeling_vae import DiagonalGaussianDistribution
+    g = torch.Generator().manual_seed(5)
+    moments = torch.randn((2, 8, 3, 4, 5), generator=g) * 3
+    moments[0, 4, 0, 0, 0], moments[0, 5, 0, 0, 0] = -100.0, 100.0      # outside the clamp
+    d = DiagonalGaussianDistribution(moments)
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    assert d.parameters is moments and torch.equal(d.mean, mean) and torch.equal(d.mode(), mean)
+    assert torch.equal(d.logvar, logvar.clamp(-30.0, 20.0))
+    assert d.logvar.min().item() == -30.0 and d.logvar.max().item() == 20.0
+    assert torch.equal(d.std, torch.exp(0.5 * d.logvar)) and torch.equal(d.var, torch.exp(d.logvar))
+    g1, g2 = torch.Generator().manual_seed(11), torch.Generator().manual_seed(11)
+    s = d.sample(generator=g1)
+    want = d.mean + d.std * torch.randn(d.mean.shape, generator=g2, dtype=moments.dtype)
+    assert torch.equal(s, want) and s.shape == mean.shape
+    assert not torch.equal(d.sample(), d.sample())                       # global RNG when no generator is given
+    det = DiagonalGaussianDistribution(moments, deterministic=True)
+    assert torch.equal(det.sample(generator=torch.Generator().manual_seed(1)), det.mean) and det.std.abs().max().item() == 0
+
+
+def test_forward_sample_posterior_uses_the_generator():
+    """forward(sample, sample_posterior=True, generator=g) (models/modeling_vae.py:114-142) = decode(posterior.sample(g))."""
+    case = dict(variant="sd21", ch=32, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None))
+    m, _ = build_model(case)
+    x = O.synthetic_video((1, 3, 5, 16, 16), 2)
+    a = m(x, sample_posterior=True, generator=torch.Generator().manual_seed(7)).sample
+    post = m.encode(x).latent_dist
+    b = m.decode(post.sample(generator=torch.Generator().manual_seed(7))).sample
+    assert torch.equal(a, b) and not torch.equal(a, m(x).sample)
+
+
+def test_in_place_weight_update_repacks():
+    """The pre-packed weight cache follows in-place parameter updates (copy_ under no_grad), like the reference modules;
+    invalidate_weights() covers writes through `.data`, which carry no version counter."""
+    case = dict(variant="sd21", ch=32, wrap=dict(tile_spatial_size=None, en_de_n_frames_a_time=None))
+    m, _ = build_model(case)
+    x = O.synthetic_video((1, 3, 1, 16, 16), 2)
+    z0 = m.encode(x).latent_dist.parameters.clone()
+    w = dict(m.named_parameters())["encoder.conv_in.weight"]
+    with torch.no_grad():
+        w.mul_(0.5)
+    z1 = m.encode(x).latent_dist.parameters.clone()
+    assert not torch.equal(z0, z1)
+    w.data.mul_(2.0)
+    m.invalidate_weights()
+    assert torch.allclose(m.encode(x).latent_dist.parameters, z0, rtol=1e-5, atol=1e-6)
+
+
+def test_chunk_tile_assembly_equals_reference_concatenation():
+    """The single-copy assembly (every (chunk, tile) result written once into the pre-allocated clip) equals the
+    reference's crop + cat over columns + cat over rows + cat over chunks (modeling_vae.py:181-191, 207-210)."""
+    case = CASES["sd21_w32_tiled"]
+    m, cfg = build_model(case)
+    x = O.synthetic_video((1, 3, 13, 104, 120), 4)         # 3 chunks x (2 x 2) tiles
+    mom = m.encode(x).latent_dist.parameters
+    g = O.TileGeometry.of(cfg)
+    outs = []
+    for n in range(3):
+        o = O._spatial_tiled(x[:, :, 4 * n:4 * n + 5], lambda t: m.encoder(t.contiguous()), g.pixel_tile, g.latent_tile, g.ratio, True)
+        outs.append(o if n == 0 else o[:, :, 1:])
+    assert torch.equal(mom, torch.cat(outs, dim=2))

@@ -3,9 +3,11 @@
 
 Gate: element-wise rtol=1e-3/atol=1e-4 is the per-operator bar (tests/test_gpu_ops.py).  Two
 differently ordered 16-bit pipelines cannot meet it end to end (the reference's own fp16 path misses it on
->60% of elements against its fp32 path), so end to end we require: error of this engine against the fp32
-golden <= 1.5 x the error of the reference algorithm evaluated in the same 16-bit dtype (oracle on torch-CUDA)
-plus a small absolute floor, for both max-abs and mean-abs.
+>60% of elements against its fp32 path), so end to end we require, against the fp32 golden of the UNMODIFIED reference:
+  (i)   max-abs and mean-abs error of this engine <= 1.0 x those of the reference algorithm evaluated in the same
+        16-bit dtype (oracle on torch-CUDA library kernels) - no slack factor, no absolute floor;
+  (ii)  the fraction of elements inside rtol=1e-3/atol=1e-4 is >= the reference-16-bit path's own fraction;
+both numbers are recorded per case (gpurun_out/e2e_*.json -> profiles/).
 """
 import json
 import os
@@ -43,11 +45,21 @@ def _err(a, b):
     return d.max().item(), d.mean().item()
 
 
+def _pass_fraction(a, gold, rtol=1e-3, atol=1e-4):
+    """Share of elements with |a - gold| <= atol + rtol |gold| (the north_star tolerance)."""
+    a, gold = a.double(), gold.double()
+    return ((a - gold).abs() <= atol + rtol * gold.abs()).double().mean().item()
+
+
+def _gate(mine, ref, what):
+    assert mine[0] <= ref[0] and mine[1] <= ref[1], f"{what}: engine error {mine} exceeds the reference-16-bit error {ref}"
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_engine_vs_reference_golden(name, dtype):
     case = CASES[name]
-    if dtype == torch.bfloat16 and not name.endswith("w128_plain"):
+    if dtype == torch.bfloat16 and "w128" not in name:
         pytest.skip("bf16 covered on the full-width cases")
     m, cfg, sd = _build(case, dtype)
     gold = np.load(os.path.join(GOLD, name + ".npz"))
@@ -71,13 +83,15 @@ def test_engine_vs_reference_golden(name, dtype):
     z_gold = g_mom[:, : cfg.z_channels].to(dtype).cuda()
     rec2 = m.decode(z_gold).sample
     mine_r2 = _err(rec2.cpu(), g_rec)
+    pf = dict(mine_moments=_pass_fraction(post.parameters.cpu(), g_mom), ref16_moments=_pass_fraction(rpost.parameters.cpu(), g_mom),
+              mine_recon=_pass_fraction(rec.cpu(), g_rec), ref16_recon=_pass_fraction(rrec.cpu(), g_rec))
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, f"e2e_{name}_{str(dtype).split('.')[-1]}.json"), "w") as f:
         json.dump(dict(mine_moments=mine_m, mine_recon=mine_r, ref16_moments=ref_m, ref16_recon=ref_r,
-                       mine_recon_from_gold_latent=mine_r2), f, indent=1)
-    floor = 2e-3 if dtype == torch.float16 else 2e-2
-    assert mine_m[0] <= 1.5 * ref_m[0] + floor and mine_m[1] <= 1.5 * ref_m[1] + floor / 10, (mine_m, ref_m)
-    assert mine_r[0] <= 1.5 * ref_r[0] + floor and mine_r[1] <= 1.5 * ref_r[1] + floor / 10, (mine_r, ref_r)
+                       mine_recon_from_gold_latent=mine_r2, pass_fraction_rtol1e_3_atol1e_4=pf), f, indent=1)
+    _gate(mine_m, ref_m, "moments")
+    _gate(mine_r, ref_r, "reconstruction")
+    assert pf["mine_moments"] >= pf["ref16_moments"] and pf["mine_recon"] >= pf["ref16_recon"], pf
     if "recon_4dlat" in gold.files:
         # 4-D latents regrouped by the model's num_latent_frames: must be the same computation as the 5-D call
         z = post.mode()
@@ -140,3 +154,29 @@ def test_cuda_graph_replay_is_bit_identical(name):
     assert len(m._graph_cache) >= 2
     m.enable_cuda_graphs(False)
     assert not m._graph_cache
+
+
+def test_compat_import_paths():
+    """The reference scripts' import lines (cvvae_inference_video.py:1, pipelines/pipeline_stable_diffusion.py:41) resolve
+    to this engine through compat/ and run: a tiny encode / decode(num_frames=1) on the GPU."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    try:
+        for n in [n for n in sys.modules if n == "models" or n.startswith("models.") or n.startswith("diffuser_engine")]:
+            del sys.modules[n]
+        A = importlib.import_module("models.modeling_vae").CVVAEModel
+        Bm = importlib.import_module("diffuser_engine.models.modeling_vae").CVVAEModel
+        import cvvae_b200
+        assert A is cvvae_b200.CVVAEModel and Bm is cvvae_b200.CVVAEModel
+        case = CASES["sd21_w32_image"]
+        m, cfg, sd = _build(case, torch.float16)
+        assert type(m) is A
+        x = O.synthetic_video(case["shape"], MANIFEST["input_seed"]).half().cuda()
+        lat = m.encode(x).latent_dist.sample(generator=torch.Generator().manual_seed(3))     # CPU generator, as pipelines pass
+        z4 = lat.permute(0, 2, 1, 3, 4).reshape(-1, lat.shape[1], *lat.shape[3:]) * m.config.scaling_factor
+        img = m.decode(z4 / m.config.scaling_factor, num_frames=1).sample                     # pipeline_stable_diffusion.py:1046
+        assert img.shape == x.shape and torch.isfinite(img).all()
+    finally:
+        sys.path.remove(os.path.join(root, "compat"))

@@ -110,7 +110,8 @@ def test_c3_sd3_bf16_chunks():
 def test_full_size_parity_against_reference_algorithm(variant, dtype, shape):
     """BASELINE configs 2 and 3 at full size: this engine vs the reference algorithm (oracle) run on the same GPU in fp32
     (library kernels, TF32 off) as the gold, with the reference algorithm in the same 16-bit dtype as the yardstick:
-    error(engine, gold) <= 1.5 x error(reference-16-bit, gold) + floor, for moments and reconstruction."""
+    error(engine, gold) <= 1.0 x error(reference-16-bit, gold) for max-abs and mean-abs of moments and reconstruction (no
+    slack, no floor), and the engine's pass fraction at rtol 1e-3 / atol 1e-4 >= the reference-16-bit path's own."""
     from cvvae_b200 import CVVAEModel, CVVAESD3Model
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -147,9 +148,14 @@ def test_full_size_parity_against_reference_algorithm(variant, dtype, shape):
     import json, os
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     os.makedirs(out, exist_ok=True)
+    def frac(a, b):
+        return ((a - b).abs() <= 1e-4 + 1e-3 * b.abs()).float().mean().item()
+
+    pf = dict(engine_moments=frac(post.parameters.float().cpu(), gold_m), reference16_moments=frac(ref_m, gold_m),
+              engine_recon=frac(rec.float().cpu(), gold_r), reference16_recon=frac(ref_r, gold_r))
     with open(os.path.join(out, f"fullsize_parity_{variant}.json"), "w") as f:
         json.dump(dict(shape=shape, dtype=str(dtype), engine_vs_fp32=dict(moments=mine_m, recon=mine_r),
-                       reference16_vs_fp32=dict(moments=r_m, recon=r_r)), f, indent=1)
-    floor = 2e-3 if dtype == torch.float16 else 2e-2
-    assert mine_m[0] <= 1.5 * r_m[0] + floor and mine_m[1] <= 1.5 * r_m[1] + floor / 10, (mine_m, r_m)
-    assert mine_r[0] <= 1.5 * r_r[0] + floor and mine_r[1] <= 1.5 * r_r[1] + floor / 10, (mine_r, r_r)
+                       reference16_vs_fp32=dict(moments=r_m, recon=r_r), pass_fraction_rtol1e_3_atol1e_4=pf), f, indent=1)
+    assert mine_m[0] <= r_m[0] and mine_m[1] <= r_m[1], (mine_m, r_m)
+    assert mine_r[0] <= r_r[0] and mine_r[1] <= r_r[1], (mine_r, r_r)
+    assert pf["engine_moments"] >= pf["reference16_moments"] and pf["engine_recon"] >= pf["reference16_recon"], pf

@@ -31,6 +31,20 @@ def _rand(shape, dtype, seed, scale=1.0):
     return ((torch.rand(shape, generator=g) * 2 - 1) * scale).to(dtype).to(DEV)
 
 
+def _assert_close(got, want, rtol, atol, tag):
+    """torch.testing.assert_close with a record of the worst offenders (gpurun_out/tol_<tag>.json) for diagnosis."""
+    err = (got - want).abs()
+    lim = atol + rtol * want.abs()
+    bad = err > lim
+    rec = {"rtol": rtol, "atol": atol, "max_abs_err": err.max().item(), "violations": int(bad.sum().item()), "numel": got.numel(),
+           "max_err_over_limit": (err / lim).max().item()}
+    if bad.any():
+        idx = torch.nonzero(bad.flatten())[:8, 0]
+        rec["worst"] = [{"i": int(i), "got": got.flatten()[i].item(), "want": want.flatten()[i].item()} for i in idx]
+    _dump(f"tol_{tag}.json", rec)
+    torch.testing.assert_close(got, want, rtol=rtol, atol=atol)
+
+
 def _dump(name, obj):
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, name), "w") as f:
@@ -57,22 +71,26 @@ def test_umma_descriptor_probe():
     from cvvae_b200 import _lib as L
     lib = L.load()
     n = 64
-    a = _rand((192, 64), torch.float16, 1)
+    a = _rand((320, 64), torch.float16, 1)
     b = _rand((n, 64), torch.float16, 2)
     res = {}
-    for shift in (0, 8, 16, 1, 3, 10, 17):
-        for mode in (0, 1):
-            out = torch.zeros((128, n), dtype=torch.float32, device=DEV)
-            L.check(lib.cvvae_probe_umma_shift(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, shift, mode,
-                                               torch.cuda.current_stream().cuda_stream), "probe")
-            torch.cuda.synchronize()
-            want = a[shift:shift + 128].float() @ b.float().t()
-            err = (out - want).abs().max().item()
-            res[f"shift{shift}_mode{mode}"] = err
+    for sbo in (8, 16):
+        for shift in (0, 8, 16, 1, 2, 3, 10, 17):
+            for mode in (0, 1):
+                out = torch.zeros((128, n), dtype=torch.float32, device=DEV)
+                L.check(lib.cvvae_probe_umma_shift(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, shift, mode, sbo,
+                                                   torch.cuda.current_stream().cuda_stream), "probe")
+                torch.cuda.synchronize()
+                rows = torch.arange(128, device=DEV)
+                src = (rows // 8) * sbo + rows % 8 + shift      # 8-row groups `sbo` slab rows apart
+                want = a[src].float() @ b.float().t()
+                err = (out - want).abs().max().item()
+                res[f"sbo{sbo}_shift{shift}_mode{mode}"] = err
     _dump("probe_umma.json", res)
     print(res)
-    for shift in (0, 8, 16):
-        assert res[f"shift{shift}_mode0"] < 1e-3, res
+    for sbo in (8, 16):
+        for shift in (0, 8, 16):
+            assert res[f"sbo{sbo}_shift{shift}_mode0"] < 1e-3, res
 
 
 CONV_CASES = {
@@ -220,7 +238,8 @@ def test_groupnorm_matches_spec(shape, per_frame, silu):
     b = _rand((shape[-1],), torch.float32, 22, 0.2)
     got = ops.groupnorm(x, g, b, 32, 1e-5, per_frame=per_frame, silu=silu)
     want = fake.groupnorm(x, g, b, 32, 1e-5, per_frame=per_frame, silu=silu, out=torch.empty(shape, dtype=torch.float32, device=DEV))
-    torch.testing.assert_close(got.float(), want, rtol=1e-3, atol=5e-4)
+    # north_star contract: rtol 1e-3 / atol 1e-4.  One rounding to fp16 costs <= 2^-11 |y| = 4.9e-4 |y| < rtol |y|.
+    _assert_close(got.float(), want, 1e-3, 1e-4, f"groupnorm_{shape[-1]}_{int(per_frame)}{int(silu)}")
     # framed (sd3) output + border replicate
     pad, inner = ops.empty_padded(*shape, torch.float16, DEV)
     ops.groupnorm(x, g, b, 32, 1e-6, per_frame=per_frame, silu=silu, out=inner)
@@ -234,14 +253,18 @@ def test_layernorm_softmax_temporal_attention():
     x = _rand((1, 5, 6, 7, 512), torch.float16, 30, 2.0)
     g = _rand((512,), torch.float32, 31) * 0.5 + 1.0
     b = _rand((512,), torch.float32, 32, 0.2)
-    torch.testing.assert_close(ops.layernorm(x, g, b, 1e-5).float(), fake.layernorm(x.float(), g, b, 1e-5), rtol=1e-3, atol=1e-3)
+    _assert_close(ops.layernorm(x, g, b, 1e-5).float(), fake.layernorm(x.float(), g, b, 1e-5).float(), 1e-3, 1e-4, "layernorm")
     s = _rand((300, 1024), torch.float32, 33, 6.0)
     p = torch.zeros((300, 1024), dtype=torch.float16, device=DEV)
     ops.softmax_rows(s, 1000, p)
     torch.testing.assert_close(p[:, :1000].float(), torch.softmax(s[:, :1000], -1), rtol=1e-3, atol=1e-5)
     q, k, v = (_rand((2, 5, 6, 7, 512), torch.float16, 34 + i) for i in range(3))
-    torch.testing.assert_close(ops.attn_temporal(q, k, v).float(), fake.attn_temporal(q.float(), k.float(), v.float()),
-                               rtol=1e-3, atol=5e-4)
+    _assert_close(ops.attn_temporal(q, k, v).float(), fake.attn_temporal(q.float(), k.float(), v.float()).float(), 1e-3, 1e-4,
+                  "attn_temporal")
+    # more latent frames than the register-resident score array holds (en_de_n_frames_a_time=None on a long clip)
+    q, k, v = (_rand((1, 40, 3, 4, 64), torch.float16, 37 + i) for i in range(3))
+    _assert_close(ops.attn_temporal(q, k, v).float(), fake.attn_temporal(q.float(), k.float(), v.float()).float(), 1e-3, 1e-4,
+                  "attn_temporal_T40")
 
 
 def test_data_movement_is_bit_exact():
@@ -286,8 +309,10 @@ def test_conv_fused_groupnorm_stats(name):
     # and GroupNorm fed with them equals GroupNorm computing its own
     g = _rand((yC,), torch.float32, 21) * 0.5 + 1.0
     b = _rand((yC,), torch.float32, 22, 0.2)
-    torch.testing.assert_close(ops.groupnorm(y, g, b, 32, 1e-5, stats=stats).float(), ops.groupnorm(y, g, b, 32, 1e-5).float(),
-                               rtol=1e-3, atol=1e-3)
+    # the two statistics differ only by the accumulation order of fp32 partial sums (relative 1e-6): the normalised
+    # outputs may differ by one fp16 rounding flip (2^-10 relative) on a few elements - inside the contract
+    _assert_close(ops.groupnorm(y, g, b, 32, 1e-5, stats=stats).float(), ops.groupnorm(y, g, b, 32, 1e-5).float(), 1e-3, 1e-4,
+                  f"gn_fused_stats_{name}")
 
 
 def test_conv_pairs_forced_everywhere():
@@ -336,3 +361,120 @@ def test_video_pre_post_processing_bit_exact(dtype):
     got8 = output_to_frames(x)
     want8 = ((torch.clamp(x, -1.0, 1.0) + 1.0) * 127.5).to(torch.uint8).squeeze(0).permute(1, 2, 3, 0)  # :47-50
     assert torch.equal(got8, want8)
+
+
+def test_batched_gemm_flags_match_per_item_calls():
+    """CVVAE_CONV_W_PER_BATCH / CVVAE_CONV_X_SHARED (the batched attention products): one launch over F frames must equal
+    F single-frame launches BIT FOR BIT (same tile plan per item) and the spec within tolerance."""
+    ops, fake = _ops(), FakeOps()
+    Fn, N, Cc = 3, 200, 128
+    ld = N
+    q = _rand((Fn, 1, 1, N, Cc), torch.float16, 70)
+    k = _rand((Fn, N, Cc), torch.float16, 71)
+    S = torch.zeros((Fn, N, ld), dtype=torch.float32, device=DEV)
+    S1 = torch.zeros_like(S)
+    ops.conv(q, k, None, alpha=Cc ** -0.5, out_f32=True, w_per_batch=True, cout=N, out=S[:, :, :N].unsqueeze(1).unsqueeze(1))
+    for f in range(Fn):
+        ops.conv(q[f:f + 1], k[f:f + 1], None, alpha=Cc ** -0.5, out_f32=True, cout=N, out=S1[f, :, :N][None, None, None])
+    assert torch.equal(S, S1)
+    Sw = torch.zeros((Fn, 1, 1, N, N), dtype=torch.float32, device=DEV)
+    fake.conv(q, k, None, alpha=Cc ** -0.5, out_f32=True, w_per_batch=True, cout=N, out=Sw)
+    torch.testing.assert_close(S.view(Fn, 1, 1, N, ld), Sw, rtol=1e-4, atol=1e-4)
+    # v^T = Wv hn^T + bv with the left operand shared by the frames and the bias along rows
+    wv = _rand((1, 1, 1, Cc, Cc), torch.float16, 72, Cc ** -0.5)
+    hn = _rand((Fn, N, Cc), torch.float16, 73)
+    bv = _rand((Cc,), torch.float32, 74, 0.2)
+    vT = torch.zeros((Fn, Cc, ld), dtype=torch.float16, device=DEV)
+    vT1 = torch.zeros_like(vT)
+    ops.conv(wv, hn, bv, bias_along_m=True, x_shared=True, w_per_batch=True, cout=N, out=vT[:, :, :N].unsqueeze(1).unsqueeze(1))
+    for f in range(Fn):
+        ops.conv(wv, hn[f:f + 1], bv, bias_along_m=True, cout=N, out=vT1[f, :, :N][None, None, None])
+    assert torch.equal(vT, vT1)
+    want = torch.zeros((Fn, 1, 1, Cc, N), dtype=torch.float32, device=DEV)
+    fake.conv(wv, hn, bv, bias_along_m=True, x_shared=True, w_per_batch=True, cout=N, out=want)
+    torch.testing.assert_close(vT.view(Fn, 1, 1, Cc, ld).float(), want, **_tol(torch.float16))
+    # O = P v, K = N with an explicit weight row stride
+    P = torch.softmax(S, dim=-1).half()
+    out = torch.zeros((Fn, 1, 1, N, Cc), dtype=torch.float16, device=DEV)
+    out1 = torch.zeros_like(out)
+    ops.conv(P[:, :, :N].unsqueeze(1).unsqueeze(1), vT, None, w_ld=ld, cout=Cc, w_per_batch=True, out=out)
+    for f in range(Fn):
+        ops.conv(P[f, :, :N][None, None, None], vT[f:f + 1], None, w_ld=ld, cout=Cc, out=out1[f:f + 1])
+    assert torch.equal(out, out1)
+
+
+def test_copy_rows_tile_assembly_is_bit_exact():
+    """The wrapper's tile assembly copy: W-contiguous NCDHW crops, 128-bit path and the unaligned element path."""
+    ops = _ops()
+    for (W, w0, ww) in ((64, 0, 48), (64, 8, 56), (61, 3, 40)):
+        src = _rand((2, 3, 5, 20, W), torch.float16, 80)
+        dst = torch.zeros((2, 3, 7, 30, 96), dtype=torch.float16, device=DEV)
+        win = dst[:, :, 2:7, 4:24, 16:16 + ww]
+        ops.copy(src[:, :, :, :, w0:w0 + ww].permute(0, 2, 3, 4, 1), win.permute(0, 2, 3, 4, 1))
+        want = torch.zeros_like(dst)
+        want[:, :, 2:7, 4:24, 16:16 + ww] = src[:, :, :, :, w0:w0 + ww]
+        assert torch.equal(dst, want)
+
+
+def test_groupnorm_statistics_are_batch_invariant():
+    """Per-frame statistics of a large frame (more positions than one CTA sweeps): the result for a sample must not depend
+    on how many samples share the launch (tile batching and sharding rely on it)."""
+    ops = _ops()
+    x = _rand((2, 2, 288, 288, 128), torch.float16, 90, 2.0)
+    g = _rand((128,), torch.float32, 91) * 0.5 + 1.0
+    b = _rand((128,), torch.float32, 92, 0.2)
+    for per_frame in (True, False):
+        both = ops.groupnorm(x, g, b, 32, 1e-5, per_frame=per_frame)
+        one = ops.groupnorm(x[1:2], g, b, 32, 1e-5, per_frame=per_frame)
+        assert torch.equal(both[1:2], one)
+
+
+def test_conv_pair_kernel_stress_is_deterministic():
+    """compute-sanitizer racecheck reports hazards in the CTA-pair kernel that we read as remote mbarrier arrivals the
+    tool does not model (profiles/r01_sanitizer.txt).  A real race would show up as run-to-run differences: 4000
+    back-to-back launches of pair kernels (odd tile counts, residual, fused statistics) under SM contention must all be
+    bit-identical to the first one and to the single-CTA kernel's result."""
+    ops, fake = _ops(), FakeOps()
+    mism = torch.zeros((), dtype=torch.int64, device=DEV)
+    for name in ("pair_n256_odd", "pair_n512"):
+        xs, Co, kernel, stride, pads, pad_t, pad_hw, up_time, ex = CONV_CASES[name]
+        B, T, H, W, Ci = xs
+        taps = kernel[0] * kernel[1] * kernel[2]
+        x = _rand(xs, torch.float16, 3)
+        w = _rand((taps, Co, Ci), torch.float16, 4, scale=(taps * Ci) ** -0.5 * 2)
+        bias = _rand((Co,), torch.float32, 5, 0.3)
+        (tl, th), (hl, hh), (wl, wh) = pads
+        yshape = (B, T + tl + th - kernel[0] + 1, H + hl + hh - kernel[1] + 1, W + wl + wh - kernel[2] + 1, Co)
+        res = _rand(yshape, torch.float16, 6) if ex.get("residual") else None
+        kw = dict(kernel=kernel, offset=(-tl, -hl, -wl), pad_t=pad_t, pad_hw=pad_hw, residual=res)
+        y0 = torch.zeros(yshape, dtype=torch.float16, device=DEV)
+        st0 = ops.new_stats(B, 32, DEV)
+        ops.conv(x, w, bias, out=y0, gn_stats=st0, gn_groups=32, **kw)
+        y = torch.zeros_like(y0)
+        st = ops.new_stats(B, 32, DEV)
+        for it in range(2000):
+            st.zero_()
+            ops.conv(x, w, bias, out=y, gn_stats=st, gn_groups=32, **kw)
+            mism += (y != y0).any().long() + (st != st0).any().long()
+    torch.cuda.synchronize()
+    assert mism.item() == 0, f"{mism.item()} of 4000 pair-kernel launches differed from the first"
+
+
+def test_ops_follow_the_tensor_device():
+    """A model on cuda:1 while cuda:0 is current (single-process multi-GPU, diffusers device placement)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ops, fake = _ops(), FakeOps()
+    assert torch.cuda.current_device() == 0
+    d1 = torch.device("cuda", 1)
+    xs, Co = (1, 2, 40, 40, 128), 256
+    x = _rand(xs, torch.float16, 3).to(d1)
+    w = _rand((27, Co, 128), torch.float16, 4, scale=(27 * 128) ** -0.5 * 2).to(d1)
+    bias = _rand((Co,), torch.float32, 5, 0.3).to(d1)
+    y = torch.zeros((1, 2, 40, 40, Co), dtype=torch.float16, device=d1)
+    kw = dict(kernel=(3, 3, 3), offset=(-1, -1, -1), pad_t=PAD_ZERO, pad_hw=PAD_ZERO)
+    ops.conv(x, w, bias, out=y, **kw)
+    want = fake.conv(x, w, bias, out=torch.zeros(y.shape, dtype=torch.float32, device=d1), **kw)
+    torch.cuda.synchronize(d1)
+    torch.testing.assert_close(y.float(), want, **_tol(torch.float16))
+    assert torch.cuda.current_device() == 0

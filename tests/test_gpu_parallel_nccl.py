@@ -42,6 +42,12 @@ def _worker(rank, world, port, ret):
         lens = [frame_range(a, b, 4)[1] - frame_range(a, b, 4)[0] for a, b in ranges]
         gathered = sh.gather_frames(x_local, lens)
         assert torch.equal(gathered, full_x)
+        for _ in range(3):   # repeated exchanges reuse the side stream / pair communicators
+            assert torch.equal(sh.encode_local(x[:, :, f0:f1].contiguous()), full_z[:, :, l0:l1])
+        from cvvae_b200.parallel import UnitShardedVAE
+        us = UnitShardedVAE(m)
+        assert torch.equal(us.encode(x), full_z), "unit-sharded encode differs from the single-GPU encode"
+        assert torch.equal(us.decode(full_z[:, :4].contiguous()), full_x), "unit-sharded decode differs"
         torch.cuda.synchronize()
         ret[rank] = "ok"
     except Exception:  # pragma: no cover

@@ -42,6 +42,24 @@ def _worker(rank, world, port, ret):
         lens = [frame_range(a, b, 4)[1] - frame_range(a, b, 4)[0] for a, b in ranges]
         gathered = sh.gather_frames(x_local, lens)
         assert torch.equal(gathered, full_x)
+        # more ranks than chunks: the tail rank owns no frames, takes no part in the halo and nobody waits for it
+        x1 = x[:, :, :5].contiguous()                      # one chunk of 4(+1) frames
+        full_z1 = m.encode(x1).latent_dist.parameters
+        r1 = chunk_ranges(1, world)
+        a, b = frame_range(*r1[rank], 4) if r1[rank][1] > r1[rank][0] else (0, 0)
+        z1 = sh.encode_local(x1[:, :, a:b].contiguous(), total_chunks=1)
+        if rank == 0:
+            assert torch.equal(z1, full_z1)
+        else:
+            assert z1.shape[2] == 0 and z1.shape[1] == full_z1.shape[1] and z1.shape[3:] == full_z1.shape[3:]
+        assert torch.equal(sh.gather_frames(z1, [full_z1.shape[2], 0]), full_z1)
+        # work-unit (chunk x tile) sharding of a clip resident on every rank
+        from cvvae_b200.parallel import UnitShardedVAE
+        us = UnitShardedVAE(m)
+        assert torch.equal(us.encode(x), full_z), "unit-sharded encode differs from single-process encode"
+        assert torch.equal(us.decode(full_z[:, :4].contiguous()), full_x), "unit-sharded decode differs"
+        x17 = x[:, :, :5]                                  # one chunk x 4 tiles: more units than ranks inside one chunk
+        assert torch.equal(us.encode(x17), m.encode(x17).latent_dist.parameters)
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback

@@ -1,7 +1,8 @@
 """ncu launch list (gpu__time_duration + dram bytes, --csv) -> per-kernel summary + the `traffic` figure bench.py reports.
 
-    python tools/summarize_launches.py gpurun_out/launches.csv profiles/r01_final
-writes <prefix>_launches_summary.csv, <prefix>_launches_full.csv (the raw list) and profiles/r01_traffic.json.
+    python tools/summarize_launches.py gpurun_out/launches.csv profiles/r02 [source_hash]
+writes <prefix>_launches_summary.csv, <prefix>_launches_full.csv (the raw list) and <prefix>_traffic.json, stamped with
+the hash of the CUDA sources the capture was taken from (bench.py flags the figure as stale when the sources change).
 """
 import collections
 import csv
@@ -18,7 +19,7 @@ def short(name):
     return name[:70]
 
 
-def main(src, prefix):
+def main(src, prefix, src_hash=None):
     with open(src) as f:
         lines = [ln for ln in f if ln.startswith('"')]
     rows = list(csv.DictReader(lines))
@@ -41,7 +42,7 @@ def main(src, prefix):
         a["wr"] += d.get("wr", 0.0)
     total = sum(a["ms"] for a in agg.values())
     with open(prefix + "_launches_summary.csv", "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1250 -c 800 --csv\n"
+        f.write(f"# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv\n"
                 f"#   command: python bench.py --steps 1 --warmup 3 --no-cpu-baseline   ({len(per)} launches, serialised, cold-cache, not power-capped:\n"
                 f"#   compare SHARES with bench.py roofline.share_of_step)\n# total {total:.2f} ms\n")
         f.write("kernel,launches,time_ms,share,dram_read_GB,dram_write_GB,GB_per_launch\n")
@@ -49,16 +50,20 @@ def main(src, prefix):
             f.write(f"\"{k}\",{a['n']},{a['ms']:.2f},{a['ms'] / total:.4f},{a['rd'] / 1e9:.2f},{a['wr'] / 1e9:.2f},"
                     f"{(a['rd'] + a['wr']) / a['n'] / 1e9:.3f}\n")
     shutil.copyfile(src, prefix + "_launches_full.csv")
-    conv = [(k, a) for k, a in agg.items() if k.startswith("conv_tc")]
+    conv = [(k, a) for k, a in agg.items() if k.startswith("conv_tc") or k.startswith("conv_stk")]
+    if src_hash is None:
+        sys.path.insert(0, ".")
+        import bench
+        src_hash = bench.source_hash()
     n = sum(a["n"] for _, a in conv)
     tot = sum(a["rd"] + a["wr"] for _, a in conv)
-    with open("profiles/r01_traffic.json", "w") as f:
+    with open(prefix + "_traffic.json", "w") as f:
         json.dump({"source": f"{prefix}_launches_summary.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum over "
                              f"{len(per)} steady-state launches of bench.py)",
                    "kernel": " + ".join(sorted({k.split('<')[0] for k, _ in conv})), "launches": n, "dram_bytes_total": tot,
-                   "dram_bytes_per_launch": tot / max(n, 1)}, f, indent=1)
+                   "dram_bytes_per_launch": tot / max(n, 1), "source_hash": src_hash}, f, indent=1)
     print(open(prefix + "_launches_summary.csv").read())
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
