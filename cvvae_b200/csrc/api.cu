@@ -105,7 +105,7 @@ extern "C" int64_t cvvae_launch_count(void) { return g_launches.load(); }
 extern "C" int cvvae_probe_umma_shift(const void* a_rows, const void* b_rows, float* out, int32_t n, int32_t row_shift,
                                       int32_t base_offset_mode, int32_t sbo_rows, void* stream_) {
   CVVAE_CHECK_ARG(a_rows && b_rows && out && n >= 16 && n <= 256 && n % 16 == 0 && row_shift >= 0 && row_shift <= 64 &&
-                      (sbo_rows == 8 || sbo_rows == 16),
+                      sbo_rows >= 8 && sbo_rows <= 16,
                   "cvvae_probe_umma_shift: bad argument");
   PFN_encodeTiled enc = get_encode_tiled();
   CVVAE_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");

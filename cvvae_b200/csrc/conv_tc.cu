@@ -50,6 +50,11 @@ struct ConvTcParams {
   int persist;  // persistent swap kernel: 256-position tiles, two TMEM stages, epilogue overlapped with the next tile
   int n_tiles;  // tiles of the whole launch (persistent kernel)
   int swap;  // operands swapped: A = weights (M = 128 output channels), B = 256 positions (Cout == 128 layers)
+  // persistent kernel, stride-1 layers: ONE slab per (kt, channel block) serves all KH x KW taps.  Tiles are 8 positions
+  // wide (one 8-row swizzle group per image row), the slab keeps PW >= 8 + KW - 1 positions per row, and the UMMA
+  // descriptor walks the image rows with SBO = PW * 128 B from a start address shifted by (kh * PW + kw) * 128 B.
+  int wide, PW;
+  uint32_t slab_stride;  // bytes between slab ring slots (slab_bytes rounded up to 1024)
   int tma_epi, box_w;  // epilogue through swizzled smem + TMA store (box_w = min(TW, 32) positions per box row)
   unsigned long long* trace;  // optional [trace_n][8] globaltimer stamps per CTA (diagnostics)
   int trace_n;
@@ -92,6 +97,19 @@ __device__ __forceinline__ void for_each_slab(const ConvTcParams& p, int t, F&& 
     for (int hg = 0; hg < p.n_hgroups; ++hg)
       for (int kw = 0; kw < p.KW; ++kw)
         for (int cb = 0; cb < p.cblocks; ++cb) f(kt, ti, hg, kw, cb);
+  }
+}
+
+// Wide-slab variant: one step per (kt, channel block).  f(kt, ti, cb)
+template <class F>
+__device__ __forceinline__ void for_each_wslab(const ConvTcParams& p, int t, F&& f) {
+  for (int kt = 0; kt < p.KT; ++kt) {
+    int ti = t * p.st + kt + p.off_t;
+    if (ti < 0 || ti >= p.T_in) {
+      if (p.pad_t == CVVAE_PAD_ZERO) continue;
+      ti = ti < 0 ? 0 : p.T_in - 1;
+    }
+    for (int cb = 0; cb < p.cblocks; ++cb) f(kt, ti, cb);
   }
 }
 
@@ -718,7 +736,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + static_cast<size_t>(p.NA) * p.slab_bytes;
+  uint8_t* sB = sA + static_cast<size_t>(p.NA) * p.slab_stride;
   uint8_t* sStage = sB + static_cast<size_t>(p.NB) * p.b_bytes;  // 8 warps x 2 x 2 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 32768);
   uint64_t* fullA = bars;          // [8]
@@ -767,11 +785,27 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
     uint32_t phase = 0;
     for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
       const TileCoord tc = decode_tile<1>(p, 0, tile);
+      if (p.wide) {
+        for_each_wslab(p, tc.t, [&](int kt, int ti, int cb) {
+          wait_bar(&emptyA[slot], phase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
+            ptx::tma_load_5d(sA + static_cast<size_t>(slot) * p.slab_stride, &tmA, &fullA[slot], cb * 64, tc.w0 + p.off_w,
+                             tc.h0 + p.off_h, ti, tc.b);
+          }
+          __syncwarp();
+          if (++slot == p.NA) {
+            slot = 0;
+            phase ^= 1;
+          }
+        });
+        continue;
+      }
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&emptyA[slot], phase ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
-          ptx::tma_load_5d(sA + static_cast<size_t>(slot) * p.slab_bytes, &tmA, &fullA[slot], cb * 64,
+          ptx::tma_load_5d(sA + static_cast<size_t>(slot) * p.slab_stride, &tmA, &fullA[slot], cb * 64,
                            tc.w0 * p.sw + kw + p.off_w, tc.h0 * p.sh + hg * p.KHs + p.off_h, ti, tc.b);
         }
         __syncwarp();
@@ -787,20 +821,27 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
     uint32_t phase = 0;
     for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
       const TileCoord tc = decode_tile<1>(p, 0, tile);
-      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
-        for (int khs = 0; khs < p.KHs; ++khs) {
-          const int tap = (kt * p.KH + hg * p.KHs + khs) * p.KW + kw;
-          wait_bar(&emptyB[slot], phase ^ 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
-            ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
-          }
-          __syncwarp();
-          if (++slot == p.NB) {
-            slot = 0;
-            phase ^= 1;
-          }
+      auto load_tap = [&](int tap, int cb) {
+        wait_bar(&emptyB[slot], phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+          ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB, &fullB[slot], cb * 64, tc.n0, tap);
         }
+        __syncwarp();
+        if (++slot == p.NB) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      if (p.wide) {
+        for_each_wslab(p, tc.t, [&](int kt, int ti, int cb) {
+          for (int kh = 0; kh < p.KH; ++kh)
+            for (int kw = 0; kw < p.KW; ++kw) load_tap((kt * p.KH + kh) * p.KW + kw, cb);
+        });
+        continue;
+      }
+      for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
+        for (int khs = 0; khs < p.KHs; ++khs) load_tap((kt * p.KH + hg * p.KHs + khs) * p.KW + kw, cb);
       });
     }
   } else if (warp == 2) {
@@ -819,11 +860,49 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
       ptx::tc_fence_after();
       const uint32_t d = tmem_base + static_cast<uint32_t>(st) * 256u;
       uint32_t accumulate = 0;
+      if (p.wide) {
+        // positions operand: 32 groups of 8 rows, one group per image row of the 8-wide tile, PW * 128 B apart
+        const uint32_t descHiX = static_cast<uint32_t>(p.PW * 8) | (1u << 14) | (2u << 29);
+        for_each_wslab(p, tc.t, [&](int kt, int ti, int cb) {
+          wait_bar(&fullA[slotA], phaseA);
+          const int ch_left = p.Cin - cb * 64;
+          const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
+          const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_stride) >> 4) & 0x3FFFu) | kDescLoFlags;
+          for (int kh = 0; kh < p.KH; ++kh) {
+            for (int kw = 0; kw < p.KW; ++kw) {
+              wait_bar(&fullB[slotB], phaseB);
+              ptx::tc_fence_after();
+              const uint32_t w_lo = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+              const uint32_t x_lo = a_lo0 + static_cast<uint32_t>(kh * p.PW + kw) * 8u;
+              if (ptx::elect_one()) {
+                for (int k = 0; k < ksteps; ++k)
+                  ptx::umma_f16_lohi2(d, w_lo + 2 * k, kDescHi, x_lo + 2 * k, descHiX, idesc, accumulate | static_cast<uint32_t>(k));
+                ptx::umma_commit(&emptyB[slotB]);
+              }
+              __syncwarp();
+              accumulate = 1;
+              if (++slotB == p.NB) {
+                slotB = 0;
+                phaseB ^= 1;
+              }
+            }
+          }
+          if (ptx::elect_one()) ptx::umma_commit(&emptyA[slotA]);
+          __syncwarp();
+          if (++slotA == p.NA) {
+            slotA = 0;
+            phaseA ^= 1;
+          }
+        });
+        if (ptx::elect_one()) ptx::umma_commit(&accFull[st]);
+        __syncwarp();
+        continue;
+      }
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&fullA[slotA], phaseA);
         const int ch_left = p.Cin - cb * 64;
         const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
-        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_stride) >> 4) & 0x3FFFu) | kDescLoFlags;
         for (int khs = 0; khs < p.KHs; ++khs) {
           wait_bar(&fullB[slotB], phaseB);
           ptx::tc_fence_after();
@@ -1024,7 +1103,7 @@ static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64
 
 // Experiment knobs (environment), read ONCE per process - nothing on the launch path calls getenv.
 struct Knobs {
-  int nacc, persist, fill, cta_group, tw, na, swap;
+  int nacc, persist, fill, cta_group, tw, na, swap, wide, pw;
   static int env(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -1032,7 +1111,7 @@ struct Knobs {
   Knobs()
       : nacc(env("CVVAE_CONV_NACC", 0)), persist(env("CVVAE_CONV_PERSIST", 1)), fill(env("CVVAE_CONV_FILL", 1)),
         cta_group(env("CVVAE_CONV_CTA_GROUP", 0)), tw(env("CVVAE_CONV_TW", 0)), na(env("CVVAE_CONV_NA", 0)),
-        swap(env("CVVAE_CONV_SWAP", 1)) {}
+        swap(env("CVVAE_CONV_SWAP", 1)), wide(env("CVVAE_CONV_WIDE", 1)), pw(env("CVVAE_CONV_PW", 0)) {}
 };
 static const Knobs& knobs() {
   static const Knobs k;
@@ -1137,6 +1216,9 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   const bool persist_want = persist_env && !flat_shape && p.Cout == 128 && N_cta == 128 && p.up_time == 1 && p.vec_ok &&
                             !(d->flags & (CVVAE_CONV_BIAS_ALONG_M | CVVAE_CONV_OUT_F32)) && y.C % 32 == 0;
   if (persist_want) p.NACC = 2;
+  // wide slabs (one slab per (kt, channel block) for all KH x KW taps): stride-1 spatial kernels of the persistent path
+  const bool wide_want = persist_want && kn.wide && kn.swap && kn.cta_group != 2 && kn.nacc == 0 && d->sh == 1 && d->sw == 1 &&
+                         d->KW > 1 && d->KW <= 3 && d->KH <= 3;
   p.flat = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1) ? 1 : 0;
   if (d->flags & (CVVAE_CONV_W_PER_BATCH | CVVAE_CONV_X_SHARED))
     CVVAE_CHECK_ARG(p.flat, "conv: batched-GEMM flags need a flat problem (H == 1, 1x1x1, stride 1)");
@@ -1177,6 +1259,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     if (tw_env >= 8 && tw_env <= 128 && (tw_env & (tw_env - 1)) == 0 && tw_env * d->sw <= 256 &&
         ((128 / tw_env) * p.NACC + p.KHs - 1) * d->sh <= 256)
       best_tw = tw_env;
+    if (wide_want) best_tw = 8;   // one 8-row swizzle group per image row of the tile
     p.TW = best_tw;
     p.ROWS = 128 / p.TW;
     p.TH = p.ROWS * p.NACC;
@@ -1191,6 +1274,15 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.NACC /= 2;
   }
   p.slab_bytes = p.flat ? static_cast<uint32_t>(p.NACC) * 16384u : static_cast<uint32_t>(p.slab_rows * p.TW) * 128u;
+  p.wide = 0;
+  p.PW = p.TW;
+  if (wide_want && !p.flat) {
+    p.wide = 1;
+    p.PW = 8 + d->KW - 1;
+    if (kn.pw > p.PW && kn.pw <= 32) p.PW = kn.pw;   // experiment knob: slab pitch in positions
+    p.slab_bytes = static_cast<uint32_t>(p.slab_rows * p.PW) * 128u;
+  }
+  p.slab_stride = (p.slab_bytes + 1023u) & ~1023u;
   // CTA pairs (cta_group::2) when there are at least two vertically adjacent tiles to pair up
   const int cg_env = kn.cta_group;
   // measured (tools/bench_conv.py): pairs help the N_cta = 256 layers (half the weight bytes per CTA, up to +10 %)
@@ -1205,17 +1297,18 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   // ---- shared memory budget: 227 KB - alignment slack - barriers
   const size_t budget = 232448 - 1024 - 1536 - (persist_want ? 32768 : 0);  // persistent kernel: own staging area
   int NB = 4;
-  while (NB > 2 && static_cast<size_t>(NB) * p.b_bytes + 2ull * p.slab_bytes > budget) --NB;
+  while (NB > 2 && static_cast<size_t>(NB) * p.b_bytes + 2ull * p.slab_stride > budget) --NB;
   size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;
-  int NA = static_cast<int>(rest / p.slab_bytes);
+  int NA = static_cast<int>(rest / p.slab_stride);
+  if (p.wide && NA > 2) NA = 2;   // a wide slab lasts KH x KW weight tiles: two slots hide its load, the rest goes to weights
   if (NA > 4) NA = 4;
   if (kn.na >= 2 && kn.na < NA) NA = kn.na;   // experiment knob: cap the slab ring (the rest goes to weight slots)
   CVVAE_CHECK_ARG(NA >= 2, "conv_tc: slab of %u bytes does not fit the shared-memory budget", p.slab_bytes);
   // spend what is left on more weight stages
-  while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_bytes <= budget) ++NB;
+  while (NB < 8 && static_cast<size_t>(NB + 1) * p.b_bytes + static_cast<size_t>(NA) * p.slab_stride <= budget) ++NB;
   p.NA = NA;
   p.NB = NB;
-  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_bytes + static_cast<size_t>(NB) * p.b_bytes + 1536 +
+  const size_t smem = 1024 + static_cast<size_t>(NA) * p.slab_stride + static_cast<size_t>(NB) * p.b_bytes + 1536 +
                       (persist_want ? 32768 : 0);
 
   // ---- tensor maps
@@ -1231,7 +1324,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     if (p.flat) {
       box[1] = 128; box[2] = 1;
     } else {
-      box[1] = (cuuint32_t)(p.TW * d->sw);
+      box[1] = (cuuint32_t)(p.wide ? p.PW : p.TW * d->sw);
       box[2] = (cuuint32_t)(p.slab_rows * d->sh);
     }
     box[3] = 1; box[4] = 1;
@@ -1252,7 +1345,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   {
     const int chalf = p.up_time == 2 ? p.Cout / 2 : p.Cout;
     const bool ok = p.vec_ok && !(d->flags & CVVAE_CONV_OUT_F32) && (p.up_time == 1 || chalf % 64 == 0) &&
-                    (static_cast<size_t>(NA) * p.slab_bytes >= 65536);
+                    (static_cast<size_t>(NA) * p.slab_stride >= 65536);
     if (ok) {
       p.box_w = p.flat ? 32 : (p.TW < 32 ? p.TW : 32);
       cuuint64_t dims[5] = {(cuuint64_t)y.C, (cuuint64_t)y.W, (cuuint64_t)y.H, (cuuint64_t)y.T, (cuuint64_t)y.B};
@@ -1292,6 +1385,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     p.gn_cpg = cpg;
   }
 
+  CVVAE_CHECK_ARG(!p.wide || p.persist, "conv_tc: internal: wide-slab plan without the persistent kernel");
   const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_hp * p.B * CG;
   CVVAE_CHECK_ARG(grid > 0 && grid < (1ll << 31), "conv_tc: grid size %lld out of range", grid);
   CVVAE_DISPATCH_DTYPE(d->dtype, {

@@ -176,7 +176,7 @@ int cvvae_abi_version(void);
 int64_t cvvae_launch_count(void);
 /* Descriptor self-test used by the GPU test-suite: runs a 128xNx64 UMMA whose A operand starts
  * `row_shift` 128-byte rows into a TMA-written SWIZZLE_128B slab of 320 rows, with the given base_offset field and
- * with consecutive 8-row groups `sbo_rows` (8 or 16) slab rows apart.  a_rows: [320][64], out: fp32 [128][N].
+ * with consecutive 8-row groups `sbo_rows` (8..16) slab rows apart.  a_rows: [320][64], out: fp32 [128][N].
  * (Decides how shifted conv taps may address one staged slab.) */
 int cvvae_probe_umma_shift(const void* a_rows, const void* b_rows, float* out, int32_t n, int32_t row_shift,
                            int32_t base_offset_mode, int32_t sbo_rows, void* stream);

@@ -74,7 +74,7 @@ def test_umma_descriptor_probe():
     a = _rand((320, 64), torch.float16, 1)
     b = _rand((n, 64), torch.float16, 2)
     res = {}
-    for sbo in (8, 16):
+    for sbo in (8, 16, 10, 12):
         for shift in (0, 8, 16, 1, 2, 3, 10, 17):
             for mode in (0, 1):
                 out = torch.zeros((128, n), dtype=torch.float32, device=DEV)
@@ -88,8 +88,10 @@ def test_umma_descriptor_probe():
                 res[f"sbo{sbo}_shift{shift}_mode{mode}"] = err
     _dump("probe_umma.json", res)
     print(res)
-    for sbo in (8, 16):
-        for shift in (0, 8, 16):
+    # what conv_tc relies on: aligned starts with dense groups (all kernels), and - for the wide-slab persistent kernel -
+    # groups 10 slab rows apart (8 + KW - 1 positions per image row) from starts shifted by kh * 10 + kw rows
+    for sbo, shifts in ((8, (0, 8, 16)), (16, (0, 8, 16)), (10, (0, 1, 2, 10, 17)), (12, (0, 1, 2))):
+        for shift in shifts:
             assert res[f"sbo{sbo}_shift{shift}_mode0"] < 1e-3, res
 
 
