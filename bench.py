@@ -70,6 +70,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sharded == un-sharded check at N > 1")
+    ap.add_argument("--shard", default="frame", choices=["frame", "unit"],
+                    help="N > 1, batch-1 configs: 'frame' = clip sharded on the frame axis + halo exchange (default; c2/c3 grow the "
+                         "clip with N), 'unit' = the FIXED clip resident on every rank, its (chunk x tile) work units dealt over "
+                         "the ranks (strong scaling of a clip with fewer chunks than GPUs)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     for k in ("frames", "height", "width", "dtype"):
@@ -345,7 +349,16 @@ def main():
     stride = 16
     F, B = args.frames, cfg["batch"]
     sharded, total_chunks = None, None
-    if cfg["scaling"] == "weak":            # c2 / c3: (F-1)/16 chunks per rank, clip of 1 + (F-1) N frames
+    unit = None
+    if args.shard == "unit" and world > 1 and B == 1:
+        from cvvae_b200.parallel import UnitShardedVAE
+        unit = UnitShardedVAE(model)
+        cfg["scaling"] = "strong"
+        total_chunks = max(1, -(-(F - 1) // stride))
+        total_frames = F
+        ranges = [(0, total_chunks)] * world
+        b_local = B
+    elif cfg["scaling"] == "weak":          # c2 / c3: (F-1)/16 chunks per rank, clip of 1 + (F-1) N frames
         cpr = (F - 1) // stride
         total_chunks = cpr * world
         total_frames = 1 + (F - 1) * world
@@ -361,7 +374,7 @@ def main():
         total_frames = F
         ranges = [(0, (F - 1) // stride)] * world
         b_local = B // world
-    if world > 1 and B == 1:
+    if world > 1 and B == 1 and unit is None:
         assert args.impl == "ours"
         sharded = FrameShardedVAE(model)
     c0, c1 = ranges[rank]
@@ -380,7 +393,7 @@ def main():
             t = min(b, hi)
         return torch.cat(parts, dim=2) if len(parts) > 1 else parts[0]
 
-    x_host = gen_chunk_frames(f0, f1, seed_base=(rank * 100 if sharded is None and world > 1 else 0)).pin_memory()
+    x_host = gen_chunk_frames(f0, f1, seed_base=(rank * 100 if (sharded is None and unit is None and world > 1) else 0)).pin_memory()
     x_dev = x_host.cuda()
 
     def step(x):
@@ -388,6 +401,8 @@ def main():
             if sharded is not None:
                 z = sharded.encode_local(x, total_chunks)[:, :zc].contiguous()
                 return sharded.decode_local(z, total_chunks)
+            if unit is not None:
+                return unit.decode(unit.encode(x)[:, :zc].contiguous())
             z = net.tiled_encode(x)[:, :zc]
             return net.tiled_decode(z)
 
@@ -412,6 +427,24 @@ def main():
 
     # ---- N > 1: sharded result == un-sharded result of the same engine, checked on rank 0 before anything is timed
     parity = None
+    if unit is not None and not args.no_parity:
+        with torch.no_grad():
+            mom_u = unit.encode(x_dev)
+            rec_u = unit.decode(mom_u[:, :zc].contiguous())
+            mom_f = model.tiled_encode(x_dev)
+            rec_f = model.tiled_decode(mom_f[:, :zc].contiguous())
+            parity = bool(torch.equal(mom_f, mom_u) and torch.equal(rec_f, rec_u))   # every rank holds the full result
+            del mom_u, rec_u, mom_f, rec_f
+        torch.cuda.empty_cache()
+        flag = torch.tensor([1 if parity else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = bool(flag.item())
+        if not parity:
+            if rank == 0:
+                print(json.dumps({"metric": cfg["metric"], "n_gpus": world, "parity_sharded": False,
+                                  "error": "unit-sharded encode/decode differs from the un-sharded run of the same engine"}))
+            dist.destroy_process_group()
+            sys.exit(1)
     if sharded is not None and not args.no_parity:
         with torch.no_grad():
             mom_l = sharded.encode_local(x_dev, total_chunks)
@@ -507,7 +540,8 @@ def main():
                 "achieved_vs_reference_count": tc["ref_flops"] / (tc["ms"] * 1e-3) / 1e12,
                 "conv_direct_ms_per_step": prof["conv_direct"]["ms"] / args.steps}
     n_tiles = len(tiles_1d(args.height)) * len(tiles_1d(args.width))
-    par = (f"frame-shard x{world}" if sharded is not None else (f"batch-shard x{world}" if world > 1 else "single GPU"))
+    par = (f"frame-shard x{world}" if sharded is not None else (f"(chunk x tile)-unit-shard x{world}" if unit is not None else
+           (f"batch-shard x{world}" if world > 1 else "single GPU")))
     line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",

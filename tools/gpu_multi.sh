@@ -1,18 +1,35 @@
 #!/bin/bash
+# Multi-GPU session:  gpurun --gpus N --timeout 1800 -- 'bash tools/gpu_multi.sh N [full]'
+# NCCL parity tests (N >= 2), then bench.py through torchrun exactly as the driver launches it; one JSON line per run in
+# gpurun_out/scale_<config>_n<N>.log.  `full`: every N in {1,2,4,8} <= the box size for c2 (weak) / c4 / c5 (strong).
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+NG=${1:-2}
 : > gpurun_out/summary_multi.txt
 run() { local name=$1; shift; local t=$1; shift
   echo "=== $name" | tee -a gpurun_out/summary_multi.txt
+  local t0=$(date +%s)
   timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
-  echo "exit $?" | tee -a gpurun_out/summary_multi.txt
-  tail -n 3 "gpurun_out/$name.log" | cut -c1-1500 | tee -a gpurun_out/summary_multi.txt; }
+  echo "exit $? ($(( $(date +%s) - t0 )) s)" | tee -a gpurun_out/summary_multi.txt
+  grep -E '^\{|passed|failed|Error' "gpurun_out/$name.log" | tail -n 2 | cut -c1-700 | tee -a gpurun_out/summary_multi.txt; }
+tr() { local n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) bench.py --gpus "$n" "$@"; }
 nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
-run bench_n1 600 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline
-run bench_n2 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3
-N=${1:-2}
-if [ "$N" -gt 2 ]; then
-run bench_n$N 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3
-run bench_ref_n$N 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 1 --warmup 0
+run nccl_tests 900 python -m pytest tests/test_gpu_parallel_nccl.py tests/test_gpu_ops.py -q -m gpu -k "nccl or tensor_device" --tb=short
+run scale_c2_n1 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-torch-baseline
+run scale_c2_n${NG} 600 tr ${NG} --steps 10 --warmup 3
+run scale_c2unit_n2 600 tr 2 --steps 10 --warmup 3 --shard unit
+run scale_c4_n${NG} 900 tr ${NG} --config c4 --steps 2 --warmup 3
+run scale_c5_n${NG} 600 tr ${NG} --config c5 --steps 3 --warmup 3
+if [ "${2:-}" = "full" ]; then
+  for n in 2 4; do
+    [ "$n" -lt "$NG" ] || continue
+    run scale_c2_n$n 600 tr $n --steps 10 --warmup 3
+    run scale_c4_n$n 900 tr $n --config c4 --steps 2 --warmup 3
+    run scale_c5_n$n 600 tr $n --config c5 --steps 3 --warmup 3
+  done
+  run scale_c3_n${NG} 600 tr ${NG} --config c3 --steps 5 --warmup 3
+  run scale_c4unit33_n${NG} 600 tr ${NG} --config c4 --frames 33 --shard unit --steps 3 --warmup 3
+else
+  run scale_c3_n${NG} 600 tr ${NG} --config c3 --steps 5 --warmup 3
 fi
