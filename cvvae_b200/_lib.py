@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cvvae_attn_temporal": (C.c_int, [_P5, _P5, _P5, _P5, C.c_int32, C.c_void_p]),
     "cvvae_replicate_border": (C.c_int, [_P5, C.c_int32, C.c_void_p]),
     "cvvae_copy5": (C.c_int, [_P5, _P5, C.c_int32, C.c_void_p]),
+    "cvvae_pack_taps_hw": (C.c_int, [_P5, _P5, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "cvvae_blend": (C.c_int, [_P5, _P5, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "cvvae_video_u8_to_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "cvvae_video_f16_to_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -92,6 +92,17 @@ def prepack_params(state_dict: Dict[str, torch.Tensor], ops, dtype: torch.dtype)
                         packed[k[: -len("weight")] + f"phase{ph}{pw}.weight"] = ops.pack_weight(wf)
                 continue
             packed[k] = ops.pack_weight(v)
+            if k in ("encoder.conv_in.weight", "decoder.conv_in.weight") and v.dim() == 5 and tuple(v.shape[3:]) == (3, 3):
+                # network-input convolutions (3 / 4 real channels): the nine spatial taps are packed into the channel axis
+                # by cvvae_pack_taps_hw, so the conv runs as KT x 1 x 1 over 9*Cin (<= 64) channels instead of 27 taps
+                # of a 95 %-empty 64-channel K block.  Weights [KT][Cout][(kh*3+kw)*Cin + ci], zero-padded to 32 / 64.
+                ci_real = state_dict[k].shape[1]
+                if 9 * ci_real <= 64:
+                    cp = 32 if 9 * ci_real <= 32 else 64
+                    w0 = state_dict[k].detach().to(dtype)
+                    wp = torch.zeros((w0.shape[2], w0.shape[0], cp), dtype=dtype, device=v.device)
+                    wp[:, :, : 9 * ci_real] = w0.permute(2, 0, 3, 4, 1).reshape(w0.shape[2], w0.shape[0], 9 * ci_real)
+                    packed[k + ".hwpack"] = wp.contiguous()
             if k == "decoder.conv_out.weight" and v.dim() == 5 and v.shape[0] <= 4 and tuple(v.shape[3:]) == (3, 3):
                 # tap-stacked form for the tiny-Cout kernel: [KT][80][Cin], row (kh*3+kw)*8 + c
                 co, ci, kt = v.shape[0], v.shape[1], v.shape[2]
@@ -178,7 +189,7 @@ class Engine:
     def conv(self, a: Act, name: str, *, kernel, stride=(1, 1, 1), pads, pad_t, pad_hw, up_time=1,
              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
              weight_key: Optional[str] = None, ref_taps: Optional[int] = None,
-             stats: Optional[torch.Tensor] = None, want_stats: bool = False) -> Act:
+             stats: Optional[torch.Tensor] = None, want_stats: bool = False, k_alg: Optional[int] = None) -> Act:
         """Convolution with the reference's padding expressed as ((t_lo,t_hi),(h_lo,h_hi),(w_lo,w_hi)).
 
         want_stats: also produce the consumer GroupNorm's (sum, sum^2) per (sample, group) in the epilogue
@@ -190,6 +201,17 @@ class Engine:
         B, T, H, W, _ = x.shape
         (tl, th), (hl, hh), (wl, wh) = pads
         kt, kh, kw = kernel
+        hwp = self.p.get(name + ".weight.hwpack") if weight_key is None else None
+        if (hwp is not None and not self._tc_ok(x) and (kh, kw) == (3, 3) and tuple(stride[1:]) == (1, 1) and up_time == 1
+                and residual is None and hasattr(self.ops, "pack_taps_hw")):
+            # network input (3 / 4 channels, NCDHW): spatial taps -> channels in one gather pass, then a KT x 1 x 1
+            # convolution on the tensor cores (the single-frame fold below then applies to the time taps as usual)
+            Ho, Wo = _out_len(H, kh, 1, hl, hh), _out_len(W, kw, 1, wl, wh)
+            xp = self.ops.empty((B, T, Ho, Wo, hwp.shape[2]), x.dtype, x.device)
+            self.ops.pack_taps_hw(x, xp, kh, kw, offset=(-hl, -wl), pad_hw=pad_hw)
+            return self.conv(Act(xp), name, kernel=(kt, 1, 1), stride=(stride[0], 1, 1), pads=((tl, th), (0, 0), (0, 0)),
+                             pad_t=pad_t, pad_hw=PAD_ZERO, out=out, weight_key=name + ".weight.hwpack", stats=stats,
+                             want_stats=want_stats, k_alg=kt * kh * kw * x.shape[4])
         if T == 1 and kt > 1 and _out_len(1, kt, stride[0], tl, th) == 1:
             # single-frame input (image path): every time tap reads frame 0 (replicate padding) or
             # nothing (zero padding), so the conv is a per-frame one with pre-summed / selected time taps; of an
@@ -252,6 +274,8 @@ class Engine:
                           residual=residual.view(B, 1, 1, P, Co) if residual is not None else None,
                           out=out.view(B, 1, 1, P, Co), **skw)
         else:
+            if k_alg is not None:
+                skw["k_alg"] = k_alg
             self.ops.conv(x, w, b, kernel=kernel, stride=stride, offset=off, pad_t=pad_t, pad_hw=pad_hw,
                           up_time=up_time, residual=residual, out=out, ref_taps=ref_taps, **skw)
         return Act(out, stats=stats)

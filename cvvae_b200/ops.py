@@ -120,7 +120,8 @@ class CudaOps:
              residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
              out_f32: bool = False, bias_along_m: bool = False, w_ld: int = 0, cout: Optional[int] = None,
              force: Optional[str] = None, ref_taps: Optional[int] = None, gn_stats: Optional[torch.Tensor] = None,
-             gn_groups: int = 32, w_per_batch: bool = False, x_shared: bool = False) -> torch.Tensor:
+             gn_groups: int = 32, w_per_batch: bool = False, x_shared: bool = False,
+             k_alg: Optional[int] = None) -> torch.Tensor:
         """y = alpha * conv(x, w) + bias + residual.  ``w`` is packed [taps, Cout, Cin(ld)].
 
         Batched GEMM (attention): ``w_per_batch`` - w is [B, Cout, Cin(ld)], one matrix per batch item of y;
@@ -169,6 +170,8 @@ class CudaOps:
         # executed: 2 * M * N * K of this launch (zero-padded taps included).  reference-dense: the same output
         # positions at the tap count the reference issues (27 for the folded up-sample phases, ref_taps)
         mn = 2 * B * t_conv * out.shape[2] * out.shape[3] * Co * Ci
+        if k_alg is not None:   # tap-packed network-input conv: count the algorithmic K (taps x real channels), not the padded one
+            mn, kt, kh, kw, ref_taps = 2 * B * t_conv * out.shape[2] * out.shape[3] * Co, k_alg, 1, 1, None
         self.profile["flops"][path] += mn * kt * kh * kw
         self.profile["ref_flops"][path] += mn * (ref_taps if ref_taps is not None else kt * kh * kw)
         # algorithmic bytes: every operand once (input, weights, residual, output)
@@ -278,6 +281,14 @@ class CudaOps:
     def copy(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         xs, ys = _t5(x), _t5(out)
         L.check(self.lib.cvvae_copy5(C.byref(xs), C.byref(ys), dtype_code(x.dtype), _stream(x)), "cvvae_copy5")
+        return out
+
+    @_on_tensor_device
+    def pack_taps_hw(self, x: torch.Tensor, out: torch.Tensor, kh: int, kw: int, offset=(0, 0), pad_hw=L.PAD_ZERO) -> torch.Tensor:
+        """out[..., (a*kw+b)*Cx + c] = x[.., h+a+off_h, w+b+off_w, c] (zero / clamped outside), remaining channels zero."""
+        xs, ys = _t5(x), _t5(out)
+        L.check(self.lib.cvvae_pack_taps_hw(C.byref(xs), C.byref(ys), kh, kw, offset[0], offset[1], pad_hw, dtype_code(out.dtype),
+                                            _stream(x)), "cvvae_pack_taps_hw")
         return out
 
     @_on_tensor_device

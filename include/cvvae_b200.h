@@ -151,6 +151,15 @@ int cvvae_replicate_border(const cvvae_tensor5* xpad, int32_t dtype, void* strea
  * channels than x, the extra channels are zero-filled (channel padding of the 3/4-channel network inputs). */
 int cvvae_copy5(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t dtype, void* stream);
 
+/* Spatial taps of a network-input convolution packed into channels (conv_in of Encoder / Decoder: 3 / 4 input channels,
+ * models/vae_models.py:731-737, 877-883; vae_models3d_sd3.py:93-99): y[b,t,h,w,(kh*KW+kw)*x.C + c] =
+ * x[b,t,h+kh+off_h,w+kw+off_w,c], zero (pad_hw = ZERO) or edge-clamped (REPLICATE) outside the image; channels of y beyond
+ * KH*KW*x.C are zero.  x: any strides (the caller's NCDHW tensor); y: channels-last, C % 8 == 0, extents = the conv's
+ * output extents in H and W.  The KT x KH x KW convolution then runs as KT x 1 x 1 over y with weights packed
+ * [KT][Cout][y.C] in the same channel order. */
+int cvvae_pack_taps_hw(const cvvae_tensor5* x, const cvvae_tensor5* y, int32_t KH, int32_t KW, int32_t off_h, int32_t off_w,
+                       int32_t pad_hw, int32_t dtype, void* stream);
+
 /* Tile blending, in place on b (models/modeling_vae.py:321-341):
  *   b[..., i] = (1 - i/ov) * a[..., La-ov+i] + (i/ov) * b[..., i]   for i in [0,ov) along axis
  * axis: 0 = width (blend_h), 1 = height (blend_v).  a and b are 5-D views with logical dims

@@ -46,7 +46,7 @@ class FakeOps:
 
     def conv(self, x, w, bias, *, kernel=(1, 1, 1), stride=(1, 1, 1), offset=(0, 0, 0), pad_t=PAD_ZERO, pad_hw=PAD_ZERO,
              up_time=1, residual=None, alpha=1.0, out=None, out_f32=False, bias_along_m=False, w_ld=0, cout=None,
-             force=None, ref_taps=None, gn_stats=None, gn_groups=32, w_per_batch=False, x_shared=False):
+             force=None, ref_taps=None, gn_stats=None, gn_groups=32, w_per_batch=False, x_shared=False, k_alg=None):
         self.launches += 1
         assert out is not None
         if w_per_batch or x_shared:
@@ -185,6 +185,20 @@ class FakeOps:
         out[..., :c] = x
         if out.shape[-1] > c:
             out[..., c:] = 0
+        return out
+
+    def pack_taps_hw(self, x, out, kh, kw, offset=(0, 0), pad_hw=PAD_ZERO):
+        self.launches += 1
+        B, T, H, W, Cx = x.shape
+        Ho, Wo = out.shape[2], out.shape[3]
+        lo_h, lo_w = -offset[0], -offset[1]
+        hi_h, hi_w = Ho + kh - 1 - H - lo_h, Wo + kw - 1 - W - lo_w
+        xin = _ncdhw(x)
+        xin = F.pad(xin.float(), (lo_w, hi_w, lo_h, hi_h, 0, 0), mode="replicate" if pad_hw == PAD_REPLICATE else "constant").to(x.dtype)
+        out.zero_()
+        for a in range(kh):
+            for b in range(kw):
+                out[..., (a * kw + b) * Cx:(a * kw + b + 1) * Cx] = xin[:, :, :, a:a + Ho, b:b + Wo].permute(0, 2, 3, 4, 1)
         return out
 
     def blend(self, a, b, overlap, axis):

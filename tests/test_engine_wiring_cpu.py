@@ -96,7 +96,8 @@ def test_single_frame_time_tap_folding(variant):
     np.testing.assert_allclose(post.parameters.numpy(), want_post.parameters.numpy(), rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(rec.numpy(), want_rec.numpy(), rtol=1e-4, atol=5e-5)
     folded = [k for k in m._engine().p if ".t1." in k and not k.endswith(".bias")]
-    assert folded and all(m._engine().p[k].shape[0] in (4, 9) for k in folded)     # 2x2 phases / 3x3: no time taps left
+    # 2x2 phases / 3x3 / tap-packed network-input convs (1 tap over 9*Cin channels): no time taps left
+    assert folded and all(m._engine().p[k].shape[0] in (4, 9) or (".hwpack" in k and m._engine().p[k].shape[0] == 1) for k in folded)
 
 
 def test_diagonal_gaussian_distribution_contract():

@@ -480,3 +480,27 @@ def test_ops_follow_the_tensor_device():
     torch.cuda.synchronize(d1)
     torch.testing.assert_close(y.float(), want, **_tol(torch.float16))
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("cin,cp,pad_hw", [(3, 32, PAD_ZERO), (3, 32, PAD_REPLICATE), (4, 64, PAD_ZERO)])
+def test_pack_taps_hw_is_bit_exact_and_conv_in_matches(cin, cp, pad_hw):
+    """Spatial taps -> channels gather of the network-input convs (bit-exact data movement), and the KT x 1 x 1 conv over
+    the packed tensor equals the 3x3x3 conv spec on the original NCDHW input."""
+    ops, fake = _ops(), FakeOps()
+    x_ncdhw = _rand((2, cin, 5, 21, 30), torch.float16, 100)
+    x = x_ncdhw.permute(0, 2, 3, 4, 1)
+    got = torch.full((2, 5, 21, 30, cp), float("nan"), dtype=torch.float16, device=DEV)
+    want = torch.empty_like(got)
+    ops.pack_taps_hw(x, got, 3, 3, offset=(-1, -1), pad_hw=pad_hw)
+    fake.pack_taps_hw(x, want, 3, 3, offset=(-1, -1), pad_hw=pad_hw)
+    assert torch.equal(got, want)
+    co = 128
+    w5 = _rand((co, cin, 3, 3, 3), torch.float16, 101, 0.2)
+    b = _rand((co,), torch.float32, 102, 0.1)
+    wp = torch.zeros((3, co, cp), dtype=torch.float16, device=DEV)
+    wp[:, :, :9 * cin] = w5.permute(2, 0, 3, 4, 1).reshape(3, co, 9 * cin)
+    y = torch.zeros((2, 5, 21, 30, co), dtype=torch.float16, device=DEV)
+    ops.conv(got, wp, b, kernel=(3, 1, 1), offset=(-2, 0, 0), pad_t=PAD_REPLICATE, out=y, force="tc")
+    ref = fake.conv(x, fake.pack_weight(w5), b, kernel=(3, 3, 3), offset=(-2, -1, -1), pad_t=PAD_REPLICATE, pad_hw=pad_hw,
+                    out=torch.zeros(y.shape, dtype=torch.float32, device=DEV))
+    torch.testing.assert_close(y.float(), ref, **_tol(torch.float16))
