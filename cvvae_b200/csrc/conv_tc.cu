@@ -1103,7 +1103,7 @@ static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64
 
 // Experiment knobs (environment), read ONCE per process - nothing on the launch path calls getenv.
 struct Knobs {
-  int nacc, persist, fill, cta_group, tw, na, swap, wide, pw;
+  int nacc, persist, fill, cta_group, tw, na, swap, wide, pw, smem_reserve;
   static int env(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -1111,7 +1111,8 @@ struct Knobs {
   Knobs()
       : nacc(env("CVVAE_CONV_NACC", 0)), persist(env("CVVAE_CONV_PERSIST", 1)), fill(env("CVVAE_CONV_FILL", 1)),
         cta_group(env("CVVAE_CONV_CTA_GROUP", 0)), tw(env("CVVAE_CONV_TW", 0)), na(env("CVVAE_CONV_NA", 0)),
-        swap(env("CVVAE_CONV_SWAP", 1)), wide(env("CVVAE_CONV_WIDE", 1)), pw(env("CVVAE_CONV_PW", 0)) {}
+        swap(env("CVVAE_CONV_SWAP", 1)), wide(env("CVVAE_CONV_WIDE", 1)), pw(env("CVVAE_CONV_PW", 0)),
+        smem_reserve(env("CVVAE_CONV_SMEM_RESERVE", 0)) {}
 };
 static const Knobs& knobs() {
   static const Knobs k;
@@ -1295,7 +1296,9 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128 * CG, N_cta);
 
   // ---- shared memory budget: 227 KB - alignment slack - barriers
-  const size_t budget = 232448 - 1024 - 1536 - (persist_want ? 32768 : 0);  // persistent kernel: own staging area
+  // (CVVAE_CONV_SMEM_RESERVE leaves shared memory free for CTAs of a memory-bound kernel from another stream to co-reside)
+  const size_t reserve = kn.smem_reserve > 0 && kn.smem_reserve <= 32768 ? static_cast<size_t>(kn.smem_reserve) : 0;
+  const size_t budget = 232448 - 1024 - 1536 - (persist_want ? 32768 : 0) - reserve;  // persistent kernel: own staging area
   int NB = 4;
   while (NB > 2 && static_cast<size_t>(NB) * p.b_bytes + 2ull * p.slab_stride > budget) --NB;
   size_t rest = budget - static_cast<size_t>(NB) * p.b_bytes;

@@ -9,14 +9,11 @@ run() { local name=$1; shift; local t=$1; shift
   local t0=$(date +%s)
   timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
   echo "exit $? ($(( $(date +%s) - t0 )) s)" | tee -a gpurun_out/summary_exp.txt
-  tail -n 6 "gpurun_out/$name.log" | cut -c1-600 | tee -a gpurun_out/summary_exp.txt; }
-run tests 1500 python -m pytest tests -m gpu -q --tb=short
-run conv_wide1 300 python tools/bench_conv.py --reps 3 --only "128 "
-CVVAE_CONV_WIDE=0 run conv_wide0 300 python tools/bench_conv.py --reps 3 --only "128 "
-CVVAE_CONV_PW=16 run conv_pw16 300 python tools/bench_conv.py --reps 3 --only "128 "
-CVVAE_CONV_PW=12 run conv_pw12 300 python tools/bench_conv.py --reps 3 --only "128 "
-run conv_5x72 300 python tools/bench_conv.py --reps 3 --only "@5x72"
-CVVAE_CONV_NACC=1 run conv_5x72_nacc1 300 python tools/bench_conv.py --reps 3 --only "@5x72"
-run bench 1200 python bench.py --steps 5 --warmup 3 --no-torch-baseline --no-cpu-baseline
-CVVAE_CONV_WIDE=0 run bench_wide0 1200 python bench.py --steps 5 --warmup 3 --no-torch-baseline --no-cpu-baseline
-run racecheck 900 compute-sanitizer --tool racecheck --racecheck-detect-level info python -m pytest tests/test_gpu_ops.py -q -x -m gpu -k "test_conv_tc_matches_spec and pair_n256_odd"
+  tail -n 3 "gpurun_out/$name.log" | cut -c1-600 | tee -a gpurun_out/summary_exp.txt; }
+run tests_pack 600 python -m pytest tests/test_gpu_ops.py -m gpu -q --tb=short -k "pack_taps or groupnorm"
+run ov_base 300 python tools/exp_overlap.py
+CVVAE_CONV_SMEM_RESERVE=8192 run ov_r8 300 python tools/exp_overlap.py
+CVVAE_CONV_SMEM_RESERVE=8192 CVVAE_GN_CTAS_PER_SM=1 run ov_r8_g1 300 python tools/exp_overlap.py
+CVVAE_CONV_SMEM_RESERVE=8192 CVVAE_GN_CTAS_PER_SM=2 run ov_r8_g2 300 python tools/exp_overlap.py
+CVVAE_CONV_SMEM_RESERVE=16384 CVVAE_GN_CTAS_PER_SM=2 run ov_r16_g2 300 python tools/exp_overlap.py
+run bench 600 python bench.py --steps 5 --warmup 3 --no-torch-baseline --no-cpu-baseline
