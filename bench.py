@@ -422,6 +422,9 @@ def main():
         sync()
         ms = torch.tensor([s.elapsed_time(e)], device="cuda")
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            timed.per_rank = [round(t.item() / steps, 2) for t in every]   # each rank's own device time per step
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
@@ -480,6 +483,7 @@ def main():
     if ops:
         ops.start_profile()
     ms_total = timed(lambda: step(x_dev), args.steps)
+    ms_per_rank = getattr(timed, "per_rank", None)
     prof = ops.stop_profile() if ops else None
     clocks = sampler.stop() if sampler else None
     launches = (ops.launch_count() - launches0) if ops else 0
@@ -556,6 +560,10 @@ def main():
             "peak_hbm_gb": peak_hbm, "source_hash": source_hash()}
     if parity is not None:
         line["parity_sharded"] = parity
+    if ms_per_rank is not None:
+        # `ms_per_step` is the MAX of these (the slowest GPU sets the pace of a weak-scaled job; power-capped B200s of one box
+        # differ by a few per cent)
+        line["ms_per_step_per_rank"] = ms_per_rank
     if roof:
         line["roofline"] = roof
     if args.impl == "ours" and world == 1:

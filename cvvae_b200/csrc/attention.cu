@@ -6,18 +6,26 @@
 
 namespace cvvae {
 
+// One CTA per row.  The row is cached in shared memory (one HBM read of the fp32 logits, one 16-bit write); 128-bit loads
+// and 64-bit stores when the row start and leading dimensions allow (the engine's buffers always do), scalar otherwise.
 template <int DT>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long ld_s, void* p_,
-                                                           long long ld_p, int cols) {
+                                                           long long ld_p, int cols, int vec) {
   using E = Elem<DT>;
-  extern __shared__ float row[];
+  extern __shared__ __align__(16) float row[];
   __shared__ float red[32];
   const long long r = blockIdx.x;
   const float* sp = s + r * ld_s;
   typename E::T* pp = reinterpret_cast<typename E::T*>(p_) + r * ld_p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cols4 = vec ? (cols >> 2) : 0;           // float4 groups handled by the vector path
   float m = -INFINITY;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+  for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(sp) + c);
+    reinterpret_cast<float4*>(row)[c] = v;
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  for (int c = cols4 * 4 + threadIdx.x; c < cols; c += blockDim.x) {
     const float v = sp[c];
     row[c] = v;
     m = fmaxf(m, v);
@@ -31,7 +39,13 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
   __syncthreads();
   float sum = 0.f;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+  for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(row)[c];
+    v.x = __expf(v.x - m); v.y = __expf(v.y - m); v.z = __expf(v.z - m); v.w = __expf(v.w - m);
+    reinterpret_cast<float4*>(row)[c] = v;
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  for (int c = cols4 * 4 + threadIdx.x; c < cols; c += blockDim.x) {
     const float e = __expf(row[c] - m);
     row[c] = e;
     sum += e;
@@ -44,7 +58,14 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 8; ++i) sum += red[i];
   const float inv = 1.0f / sum;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) pp[c] = E::from_f(row[c] * inv);
+  for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
+    const float4 v = reinterpret_cast<float4*>(row)[c];
+    uint2 o;
+    o.x = E::pack2(v.x * inv, v.y * inv);
+    o.y = E::pack2(v.z * inv, v.w * inv);
+    reinterpret_cast<uint2*>(pp)[c] = o;
+  }
+  for (int c = cols4 * 4 + threadIdx.x; c < cols; c += blockDim.x) pp[c] = E::from_f(row[c] * inv);
 }
 
 struct TAttnParams {
@@ -145,7 +166,9 @@ extern "C" int cvvae_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t
       CVVAE_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr.mark();
     }
-    softmax_rows_kernel<DT><<<static_cast<unsigned>(rows), 256, smem, stream>>>(s, ld_s, p, ld_p, cols);
+    const int vec = (ld_s % 4 == 0) && (ld_p % 4 == 0) && (reinterpret_cast<uintptr_t>(s) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(p) % 8 == 0);
+    softmax_rows_kernel<DT><<<static_cast<unsigned>(rows), 256, smem, stream>>>(s, ld_s, p, ld_p, cols, vec);
   });
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;

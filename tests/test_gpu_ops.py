@@ -504,3 +504,52 @@ def test_pack_taps_hw_is_bit_exact_and_conv_in_matches(cin, cp, pad_hw):
     ref = fake.conv(x, fake.pack_weight(w5), b, kernel=(3, 3, 3), offset=(-2, -1, -1), pad_t=PAD_REPLICATE, pad_hw=pad_hw,
                     out=torch.zeros(y.shape, dtype=torch.float32, device=DEV))
     torch.testing.assert_close(y.float(), ref, **_tol(torch.float16))
+
+
+@pytest.mark.parametrize("src,dst", [((90, 120), (72, 96)), ((72, 128), (57, 101)), ((60, 80), (120, 160)), ((720, 1280), (576, 1024))])
+def test_gpu_resize_matches_torchvision(src, dst):
+    """GPU antialiased bilinear resize of the inference script (transforms.Resize on uint8 frames): within 1 LSB of
+    torchvision's CPU result (its 16-bit fixed-point weights deviate from exact arithmetic on < 1 % of the pixels), and the
+    fused resize+normalise pass equals normalising the resized frames bit for bit."""
+    from torchvision import transforms
+    from cvvae_b200.video_io import frames_to_input, resize_frames
+    g = torch.Generator().manual_seed(70)
+    T = 3 if src[0] < 700 else 2
+    frames = torch.randint(0, 256, (T, src[0], src[1], 3), generator=g, dtype=torch.uint8)
+    want = transforms.Resize(size=dst)(frames.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)       # cvvae_inference_video.py:24-28
+    got = resize_frames(frames.to(DEV), dst)
+    d = (got.cpu().int() - want.int()).abs()
+    assert got.shape == want.shape and d.max().item() <= 1, d.max().item()
+    assert (d > 0).float().mean().item() < 0.02
+    fused = frames_to_input(frames.to(DEV), torch.float16, size=dst)
+    assert torch.equal(fused, frames_to_input(got, torch.float16))
+
+
+def test_groupnorm_fixed_point_statistics_at_large_magnitudes():
+    """The int64 fixed-point accumulators (sum * 2^20, sum of squares * 2^18; common.cuh) at the magnitudes a trained
+    checkpoint could produce: activations of rms ~1.2e3 over a full-resolution chunk-tile (5.6 M positions per group: the
+    documented range is |sum| < 8.8e12, sum^2 < 3.5e13) - no overflow, statistics exact to fp64, and the same through the
+    convolution epilogue's fused sums."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(110)
+    x = ((torch.rand((1, 17, 576, 576, 32), generator=g) * 2 - 1) * 2000.0 + 300.0).to(torch.float16).to(DEV)
+    gam = _rand((32,), torch.float32, 111) * 0.5 + 1.0
+    bet = _rand((32,), torch.float32, 112, 0.2)
+    got = ops.groupnorm(x, gam, bet, 32, 1e-5, silu=False)
+    xd = x.double()
+    mean = xd.mean(dim=(1, 2, 3), keepdim=True)
+    var = xd.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    want = ((xd - mean) / torch.sqrt(var + 1e-5) * gam.double() + bet.double()).float()
+    _assert_close(got.float(), want, 1e-3, 1e-4, "groupnorm_large_magnitude")
+    del xd, want, got
+    # conv epilogue: outputs of magnitude ~1e3 (weights scaled up), statistics vs fp64 sums of the stored tensor
+    xs = _rand((1, 2, 64, 48, 128), torch.float16, 113)
+    w = _rand((9, 128, 128), torch.float16, 114, scale=30.0)
+    y = torch.zeros((1, 2, 64, 48, 128), dtype=torch.float16, device=DEV)
+    st = ops.new_stats(1, 32, DEV)
+    ops.conv(xs, w, None, kernel=(1, 3, 3), offset=(0, -1, -1), out=y, gn_stats=st, gn_groups=32)
+    v = y.double().reshape(1, -1, 32, 4)
+    assert torch.isfinite(y).all() and y.abs().max().item() > 500
+    want_s = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
+    got_s = torch.stack([st[..., 0].double() / 2.0 ** 20, st[..., 1].double() / 2.0 ** 18], dim=-1)
+    torch.testing.assert_close(got_s, want_s, rtol=1e-5, atol=1.0)
