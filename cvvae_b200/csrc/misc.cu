@@ -95,60 +95,55 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const V5 x, const V5 y, 
 // Spatial taps packed into channels: y[b,t,h,w,(kh*KW+kw)*Cx + c] = x[b,t,h+kh+off_h,w+kw+off_w,c] (zero or clamped outside
 // the image), channels beyond KH*KW*Cx zero.  Turns the KT x KH x KW convolution of a network INPUT (3 / 4 channels, where a
 // 64-channel K block per tap would be 95 % zeros) into a KT x 1 x 1 convolution over KH*KW*Cx (<= 64) channels.
-// One CTA per (b, t, h, segment of 256 / (y.C/8) positions along w): the KH input rows x Cx channels of the segment (plus
-// the KW - 1 halo positions) are staged in shared memory with coalesced loads along w (x is read through its strides: the
-// caller's NCDHW tensor), then each thread assembles one 16-byte vector of 8 packed channels.
+// One thread per (position, 8-channel vector) of y, consecutive threads walking w (coalesced 2-byte loads per tap through
+// x's strides - the caller's NCDHW tensor - and coalesced 16-byte stores).  A thread's vector index is loop-invariant
+// (the grid stride is a multiple of y.C/8), so the (dh, dw, channel) source of each of its 8 channels is resolved once.
+// (A shared-memory staged variant measured slower: 1.75 vs 1.38 ms per step; the loads hit L1/L2, the stores dominate.)
 __global__ void __launch_bounds__(256) pack_taps_hw_kernel(const V5 x, const V5 y, int KH, int KW, int off_h, int off_w,
-                                                           int replicate, int segs) {
-  extern __shared__ uint16_t s_in[];   // [KH][Cx][seg + KW - 1]
+                                                           int replicate) {
   const int vecs = y.C >> 3;
-  const int seg = 256 / vecs;          // positions per CTA
-  const int pitch = seg + KW - 1;
-  long long r = blockIdx.x;
-  const int sg = static_cast<int>(r % segs); r /= segs;
-  const int h = static_cast<int>(r % y.H); r /= y.H;
-  const int t = static_cast<int>(r % y.T); r /= y.T;
-  const int b = static_cast<int>(r);
-  const int w0 = sg * seg;
-  const uint16_t* xb = reinterpret_cast<const uint16_t*>(x.ptr) + b * x.s_b + t * x.s_t;
-  const int n_in = KH * x.C * pitch;
-  for (int i = threadIdx.x; i < n_in; i += 256) {
-    const int wl = i % pitch;
-    const int c = (i / pitch) % x.C;
-    const int kh = i / (pitch * x.C);
-    int hi = h + kh + off_h, wi = w0 + wl + off_w;
-    uint16_t val = 0;
-    bool ok = true;
-    if (replicate) {
-      hi = min(max(hi, 0), x.H - 1);
-      wi = min(max(wi, 0), x.W - 1);
-    } else {
-      ok = hi >= 0 && hi < x.H && wi >= 0 && wi < x.W;
-    }
-    if (ok) val = __ldg(xb + hi * x.s_h + wi * x.s_w + c * x.s_c);
-    s_in[i] = val;
-  }
-  __syncthreads();
-  const int v = threadIdx.x % vecs, wl = threadIdx.x / vecs, w = w0 + wl;
-  if (w >= y.W) return;
+  const long long n = 1ll * y.B * y.T * y.H * y.W * vecs;
   const int used = KH * KW * x.C;
-  uint16_t o[8];
+  const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int v = static_cast<int>(i0 % vecs);     // invariant: gridDim.x * 256 % vecs == 0 (vecs divides 256)
+  int dh[8], dw[8];
+  long long dc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = v * 8 + j;
-    uint16_t val = 0;
-    if (ch < used) {
-      const int tap = ch / x.C, c = ch - tap * x.C;
-      val = s_in[((tap / KW) * x.C + c) * pitch + wl + tap % KW];
-    }
-    o[j] = val;
+    const int tap = ch < used ? ch / x.C : 0;
+    dh[j] = ch < used ? tap / KW + off_h : -(1 << 20);   // far outside: contributes zero (never clamped: see below)
+    dw[j] = tap % KW + off_w;
+    dc[j] = ch < used ? (ch - tap * x.C) * x.s_c : 0;
   }
-  uint4 pk;
-  pk.x = o[0] | (static_cast<uint32_t>(o[1]) << 16);
-  pk.y = o[2] | (static_cast<uint32_t>(o[3]) << 16);
-  pk.z = o[4] | (static_cast<uint32_t>(o[5]) << 16);
-  pk.w = o[6] | (static_cast<uint32_t>(o[7]) << 16);
-  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y.ptr) + b * y.s_b + t * y.s_t + h * y.s_h + w * y.s_w + v * 8) = pk;
+  for (long long i = i0; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i / vecs;
+    const int w = static_cast<int>(r % y.W); r /= y.W;
+    const int h = static_cast<int>(r % y.H); r /= y.H;
+    const int t = static_cast<int>(r % y.T); r /= y.T;
+    const int b = static_cast<int>(r);
+    const uint16_t* xb = reinterpret_cast<const uint16_t*>(x.ptr) + b * x.s_b + t * x.s_t;
+    uint16_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int hi = h + dh[j], wi = w + dw[j];
+      const bool pad_ch = dh[j] < -(1 << 19);
+      bool ok = !pad_ch;
+      if (replicate && ok) {
+        hi = min(max(hi, 0), x.H - 1);
+        wi = min(max(wi, 0), x.W - 1);
+      } else {
+        ok = ok && hi >= 0 && hi < x.H && wi >= 0 && wi < x.W;
+      }
+      o[j] = ok ? __ldg(xb + hi * x.s_h + wi * x.s_w + dc[j]) : static_cast<uint16_t>(0);
+    }
+    uint4 pk;
+    pk.x = o[0] | (static_cast<uint32_t>(o[1]) << 16);
+    pk.y = o[2] | (static_cast<uint32_t>(o[3]) << 16);
+    pk.z = o[4] | (static_cast<uint32_t>(o[5]) << 16);
+    pk.w = o[6] | (static_cast<uint32_t>(o[7]) << 16);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y.ptr) + b * y.s_b + t * y.s_t + h * y.s_h + w * y.s_w + v * 8) = pk;
+  }
 }
 
 // b[.., i ..] = (1 - i/ov) * a[.., La-ov+i ..] + (i/ov) * b[.., i ..], fp32 math, one rounding
@@ -237,15 +232,10 @@ extern "C" int cvvae_pack_taps_hw(const cvvae_tensor5* x, const cvvae_tensor5* y
                   y->C, KH * KW, x->C);
   CVVAE_CHECK_ARG(vec8_ok(y), "cvvae_pack_taps_hw: y must be a 16-byte aligned channels-last view with C %% 8 == 0");
   const int vecs = y->C / 8;
-  CVVAE_CHECK_ARG(vecs <= 32 && 256 % vecs == 0, "cvvae_pack_taps_hw: y.C = %d unsupported (8..256 in steps dividing 2048)", y->C);
-  const int seg = 256 / vecs;
-  const int segs = (y->W + seg - 1) / seg;
-  const long long blocks = 1ll * y->B * y->T * y->H * segs;
-  CVVAE_CHECK_ARG(blocks < (1ll << 31), "cvvae_pack_taps_hw: too many rows");
-  const size_t smem = sizeof(uint16_t) * KH * x->C * (seg + KW - 1);
-  CVVAE_CHECK_ARG(smem <= 48 * 1024, "cvvae_pack_taps_hw: x.C = %d too wide for the staging tile", x->C);
-  pack_taps_hw_kernel<<<static_cast<unsigned>(blocks), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      mk(x), mk(y), KH, KW, off_h, off_w, pad_hw == CVVAE_PAD_REPLICATE ? 1 : 0, segs);
+  CVVAE_CHECK_ARG(vecs <= 32 && 256 % vecs == 0, "cvvae_pack_taps_hw: y.C = %d unsupported (C/8 must divide 256)", y->C);
+  const long long n = 1ll * y->B * y->T * y->H * y->W * vecs;
+  pack_taps_hw_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(x), mk(y), KH, KW, off_h, off_w,
+                                                                                 pad_hw == CVVAE_PAD_REPLICATE ? 1 : 0);
   CVVAE_LAUNCH_CHECK();
   return CVVAE_OK;
 }

@@ -509,8 +509,9 @@ def test_pack_taps_hw_is_bit_exact_and_conv_in_matches(cin, cp, pad_hw):
 @pytest.mark.parametrize("src,dst", [((90, 120), (72, 96)), ((72, 128), (57, 101)), ((60, 80), (120, 160)), ((720, 1280), (576, 1024))])
 def test_gpu_resize_matches_torchvision(src, dst):
     """GPU antialiased bilinear resize of the inference script (transforms.Resize on uint8 frames): within 1 LSB of
-    torchvision's CPU result (its 16-bit fixed-point weights deviate from exact arithmetic on < 1 % of the pixels), and the
-    fused resize+normalise pass equals normalising the resized frames bit for bit."""
+    torchvision's CPU result (its 16-bit fixed-point weights deviate from exact arithmetic on < 1 % of the pixels for
+    generic ratios and on 3-4 % for exact 2x up-scaling, where a quarter of the exact results are .5 ties), and the fused
+    resize+normalise pass equals normalising the resized frames bit for bit."""
     from torchvision import transforms
     from cvvae_b200.video_io import frames_to_input, resize_frames
     g = torch.Generator().manual_seed(70)
@@ -520,7 +521,7 @@ def test_gpu_resize_matches_torchvision(src, dst):
     got = resize_frames(frames.to(DEV), dst)
     d = (got.cpu().int() - want.int()).abs()
     assert got.shape == want.shape and d.max().item() <= 1, d.max().item()
-    assert (d > 0).float().mean().item() < 0.02
+    assert (d > 0).float().mean().item() < (0.06 if dst[0] == 2 * src[0] else 0.02)
     fused = frames_to_input(frames.to(DEV), torch.float16, size=dst)
     assert torch.equal(fused, frames_to_input(got, torch.float16))
 
