@@ -12,7 +12,7 @@ from ._build import LIBPATH
 F16, BF16 = 0, 1
 PAD_ZERO, PAD_REPLICATE = 0, 1
 CONV_BIAS_ALONG_M, CONV_FORCE_DIRECT, CONV_OUT_F32, CONV_W_PER_BATCH, CONV_X_SHARED = 1, 2, 4, 8, 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Tensor5(C.Structure):
@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("up_time", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_int32),
         ("alpha", C.c_float),
         ("gn_stats", C.c_void_p), ("gn_groups", C.c_int32),
+        ("x2", Tensor5), ("w2", C.c_void_p),
     ]
 
 

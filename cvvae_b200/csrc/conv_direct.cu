@@ -118,8 +118,8 @@ int conv_direct_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   CVVAE_CHECK_ARG(y.B == x.B, "conv: batch mismatch");
   CVVAE_CHECK_ARG(y.C == (p.up_time == 2 ? d->Cout / 2 : d->Cout), "conv: y.C %d inconsistent with Cout %d / up_time %d",
                   y.C, d->Cout, p.up_time);
-  if (d->flags & (CVVAE_CONV_W_PER_BATCH | CVVAE_CONV_X_SHARED)) {
-    set_error("conv_direct: the batched-GEMM flags are a tensor-core path feature");
+  if ((d->flags & (CVVAE_CONV_W_PER_BATCH | CVVAE_CONV_X_SHARED)) || d->w2) {
+    set_error("conv_direct: the batched-GEMM flags and the fused shortcut are tensor-core path features");
     return CVVAE_E_UNSUPPORTED;
   }
   if (d->gn_stats) {

@@ -56,6 +56,10 @@ struct ConvTcParams {
   int wide, PW;
   uint32_t slab_stride;  // bytes between slab ring slots (slab_bytes rounded up to 1024)
   int tma_epi, box_w;  // epilogue through swizzled smem + TMA store (box_w = min(TW, 32) positions per box row)
+  // fused 1x1 shortcut (ResnetBlock3D nin_shortcut / conv_shortcut as extra K steps of conv2): cblocks2 64-channel blocks
+  // of a second input tensor (same positions as the output) times a [Cout][Cin2] matrix, accumulated after the taps
+  int Cin2, cblocks2;
+  uint32_t sc_off16;  // wide slabs: descriptor offset (>> 4) of the centre tap inside the slab
   unsigned long long* trace;  // optional [trace_n][8] globaltimer stamps per CTA (diagnostics)
   int trace_n;
 };
@@ -120,6 +124,7 @@ template <int DT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                    const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -217,6 +222,25 @@ __global__ void __launch_bounds__(kThreads, 1)
           phase ^= 1;
         }
       });
+      // fused 1x1 shortcut: the (unshifted) window of the second input, one slab per 64-channel block
+      for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {
+        wait_bar(&emptyA[slot], phase ^ 1);
+        uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_bytes;
+        if (ptx::elect_one()) {
+          if (CG == 2) {
+            if (rank == 0) ptx::mbar_expect_tx(&fullA[slot], 2u * p.slab_bytes);
+            ptx::tma_load_5d_cg2(dst, &tmA2, ptx::mapa_u32(ptx::smem_u32(&fullA[slot]), 0), cb2 * 64, tc.w0, tc.h0, tc.t, xb);
+          } else {
+            ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
+            ptx::tma_load_5d(dst, &tmA2, &fullA[slot], cb2 * 64, tc.w0, tc.h0, tc.t, xb);
+          }
+        }
+        __syncwarp();
+        if (++slot == p.NA) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- B producer
@@ -246,6 +270,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       });
+      for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {   // shortcut weights [Cout][Cin2]
+        wait_bar(&emptyB[slot], phase ^ 1);
+        if (ptx::elect_one()) {
+          if (CG == 2) {
+            if (rank == 0) ptx::mbar_expect_tx(&fullB[slot], 2u * p.b_bytes);
+            ptx::tma_load_3d_cg2(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB2, ptx::mapa_u32(ptx::smem_u32(&fullB[slot]), 0),
+                                 cb2 * 64, tc.n0 + rank * (p.N_cta / 2), 0);
+          } else {
+            ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+            ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB2, &fullB[slot], cb2 * 64, tc.n0, 0);
+          }
+        }
+        __syncwarp();
+        if (++slot == p.NB) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
     }
   } else if (warp == 2 && rank == 0) {
     // ------------------------------------------------------------- MMA issuer (the pair's leader when CG = 2)
@@ -327,6 +369,42 @@ __global__ void __launch_bounds__(kThreads, 1)
           phaseA ^= 1;
         }
       });
+      for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {   // fused 1x1 shortcut: row-tap 0 of the unshifted window
+        wait_bar(&fullA[slotA], phaseA);
+        wait_bar(&fullB[slotB], phaseB);
+        ptx::tc_fence_after();
+        const int ch_left = p.Cin2 - cb2 * 64;
+        const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
+        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+        const uint32_t b_lo0 = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+        if (ptx::elect_one()) {
+          for (int s = 0; s < nacc_eff; ++s) {
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(s) * sub_stride16;
+            const uint32_t d = tmem_base + static_cast<uint32_t>(s) * ncta;
+            for (int k = 0; k < ksteps; ++k) {
+              if (CG == 2) ptx::umma_f16_lohi_cg2(d, a_lo + 2 * k, b_lo0 + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+              else ptx::umma_f16_lohi(d, a_lo + 2 * k, b_lo0 + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+            }
+          }
+          if (CG == 2) {
+            ptx::umma_commit_pair(&emptyB[slotB]);
+            ptx::umma_commit_pair(&emptyA[slotA]);
+          } else {
+            ptx::umma_commit(&emptyB[slotB]);
+            ptx::umma_commit(&emptyA[slotA]);
+          }
+        }
+        __syncwarp();
+        accumulate = 1;
+        if (++slotB == p.NB) {
+          slotB = 0;
+          phaseB ^= 1;
+        }
+        if (++slotA == p.NA) {
+          slotA = 0;
+          phaseA ^= 1;
+        }
+      }
       if (ptx::elect_one()) {
         if (CG == 2) ptx::umma_commit_pair(accFull); else ptx::umma_commit(accFull);
       }
@@ -731,6 +809,7 @@ template <int DT>
 __global__ void __launch_bounds__(kPersistThreads, 1)
     conv_tc_psw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                        const ConvTcParams p) {
   using E = Elem<DT>;
   extern __shared__ uint8_t smem_raw[];
@@ -799,6 +878,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
             phase ^= 1;
           }
         });
+        for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {   // fused 1x1 shortcut: same window (with its halo) of the second input
+          wait_bar(&emptyA[slot], phase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
+            ptx::tma_load_5d(sA + static_cast<size_t>(slot) * p.slab_stride, &tmA2, &fullA[slot], cb2 * 64, tc.w0 + p.off_w,
+                             tc.h0 + p.off_h, tc.t, tc.b);
+          }
+          __syncwarp();
+          if (++slot == p.NA) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
         continue;
       }
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
@@ -838,6 +930,18 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
           for (int kh = 0; kh < p.KH; ++kh)
             for (int kw = 0; kw < p.KW; ++kw) load_tap((kt * p.KH + kh) * p.KW + kw, cb);
         });
+        for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {   // shortcut weights [Cout][Cin2]
+          wait_bar(&emptyB[slot], phase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+            ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, &tmB2, &fullB[slot], cb2 * 64, tc.n0, 0);
+          }
+          __syncwarp();
+          if (++slot == p.NB) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
         continue;
       }
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
@@ -894,6 +998,31 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
             phaseA ^= 1;
           }
         });
+        for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {   // fused 1x1 shortcut: the centre tap of the second input's slab
+          wait_bar(&fullA[slotA], phaseA);
+          wait_bar(&fullB[slotB], phaseB);
+          ptx::tc_fence_after();
+          const int ch_left = p.Cin2 - cb2 * 64;
+          const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
+          const uint32_t x_lo = (((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_stride) >> 4) & 0x3FFFu) | kDescLoFlags) + p.sc_off16;
+          const uint32_t w_lo = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+          if (ptx::elect_one()) {
+            for (int k = 0; k < ksteps; ++k)
+              ptx::umma_f16_lohi2(d, w_lo + 2 * k, kDescHi, x_lo + 2 * k, descHiX, idesc, accumulate | static_cast<uint32_t>(k));
+            ptx::umma_commit(&emptyB[slotB]);
+            ptx::umma_commit(&emptyA[slotA]);
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (++slotB == p.NB) {
+            slotB = 0;
+            phaseB ^= 1;
+          }
+          if (++slotA == p.NA) {
+            slotA = 0;
+            phaseA ^= 1;
+          }
+        }
         if (ptx::elect_one()) ptx::umma_commit(&accFull[st]);
         __syncwarp();
         continue;
@@ -1342,6 +1471,46 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     if (!encode_map(&tmB, d->w, 3, dims, strides, box, estr)) return CVVAE_E_CUDA;
   }
 
+  // ---- fused 1x1 shortcut: a second input tensor (same positions as the output) and a [Cout][Cin2] matrix
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  p.Cin2 = 0;
+  p.cblocks2 = 0;
+  p.sc_off16 = 0;
+  if (d->w2) {
+    const cvvae_tensor5& x2 = d->x2;
+    CVVAE_CHECK_ARG(tensor_ok(&x2) && x2.B == y.B && x2.T == y.T && x2.H == y.H && x2.W == y.W,
+                    "conv: fused shortcut input must have the output's [B,T,H,W] extents");
+    CVVAE_CHECK_ARG(x2.s_c == 1 && x2.C % 8 == 0 && !(x2.s_w % 8) && !(x2.s_h % 8) && !(x2.s_t % 8) && !(x2.s_b % 8) &&
+                        reinterpret_cast<uintptr_t>(x2.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(d->w2) % 16 == 0,
+                    "conv: fused shortcut operands must be 16-byte aligned channels-last views with C %% 8 == 0");
+    CVVAE_CHECK_ARG(!p.flat && p.up_time == 1 && d->st == 1 && d->sh == 1 && d->sw == 1 && !d->residual &&
+                        !(d->flags & (CVVAE_CONV_BIAS_ALONG_M | CVVAE_CONV_OUT_F32 | CVVAE_CONV_W_PER_BATCH | CVVAE_CONV_X_SHARED)),
+                    "conv: a fused shortcut needs a stride-1 spatial convolution without residual / interleave");
+    CVVAE_CHECK_ARG(-d->off_h >= 0 && -d->off_h < d->KH && -d->off_w >= 0 && -d->off_w < d->KW && d->off_t <= 0 && -d->off_t < d->KT,
+                    "conv: fused shortcut needs the centre tap inside the kernel window");
+    if (persist_want && !p.wide) {
+      set_error("conv_tc: fused shortcut unsupported on the non-wide persistent path");
+      return CVVAE_E_UNSUPPORTED;
+    }
+    p.Cin2 = x2.C;
+    p.cblocks2 = (x2.C + 63) / 64;
+    if (p.wide) p.sc_off16 = static_cast<uint32_t>((-d->off_h) * p.PW + (-d->off_w)) * 8u;
+    {
+      cuuint64_t dims[5] = {(cuuint64_t)x2.C, (cuuint64_t)x2.W, (cuuint64_t)x2.H, (cuuint64_t)x2.T, (cuuint64_t)x2.B};
+      cuuint64_t strides[4] = {(cuuint64_t)x2.s_w * 2, (cuuint64_t)x2.s_h * 2, (cuuint64_t)x2.s_t * 2, (cuuint64_t)x2.s_b * 2};
+      for (int i = 0; i < 4; ++i)
+        if (dims[i + 1] == 1 && (strides[i] == 0 || strides[i] % 16)) strides[i] = (cuuint64_t)x2.C * 2;
+      cuuint32_t box[5] = {64, (cuuint32_t)(p.wide ? p.PW : p.TW), (cuuint32_t)p.slab_rows, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+      if (!encode_map(&tmA2, x2.ptr, 5, dims, strides, box, estr)) return CVVAE_E_CUDA;
+    }
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)x2.C, (cuuint64_t)p.Cout, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)x2.C * 2, (cuuint64_t)x2.C * p.Cout * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)(N_cta / CG), 1}, estr[3] = {1, 1, 1};
+      if (!encode_map(&tmB2, d->w2, 3, dims, strides, box, estr)) return CVVAE_E_CUDA;
+    }
+  }
+
   // ---- epilogue through shared memory + TMA store where the output is a plain channels-last 16-bit tensor
   CUtensorMap tmY = tmA, tmR = tmA;
   p.tma_epi = 0;
@@ -1389,6 +1558,10 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   }
 
   CVVAE_CHECK_ARG(!p.wide || p.persist, "conv_tc: internal: wide-slab plan without the persistent kernel");
+  if (p.cblocks2 && p.swap && !p.persist) {
+    set_error("conv_tc: fused shortcut unsupported on the non-persistent operand-swapped path");
+    return CVVAE_E_UNSUPPORTED;
+  }
   const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_hp * p.B * CG;
   CVVAE_CHECK_ARG(grid > 0 && grid < (1ll << 31), "conv_tc: grid size %lld out of range", grid);
   CVVAE_DISPATCH_DTYPE(d->dtype, {
@@ -1402,7 +1575,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     if (p.persist) {
       p.n_tiles = static_cast<int>(grid);
       const int ctas = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-      conv_tc_psw_kernel<DT><<<ctas, kPersistThreads, smem, stream>>>(tmA, tmB, tmY, tmR, p);
+      conv_tc_psw_kernel<DT><<<ctas, kPersistThreads, smem, stream>>>(tmA, tmB, tmY, tmR, tmA2, tmB2, p);
     } else if (CG == 2) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -1416,9 +1589,9 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      CVVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<DT, 2>, tmA, tmB, tmY, tmR, p));
+      CVVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<DT, 2>, tmA, tmB, tmY, tmR, tmA2, tmB2, p));
     } else {
-      conv_tc_kernel<DT, 1><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(tmA, tmB, tmY, tmR, p);
+      conv_tc_kernel<DT, 1><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(tmA, tmB, tmY, tmR, tmA2, tmB2, p);
     }
   });
   CVVAE_LAUNCH_CHECK();

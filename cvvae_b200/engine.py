@@ -18,6 +18,7 @@ All arithmetic goes through an ``ops`` backend (``cvvae_b200.ops.CudaOps`` in pr
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -129,6 +130,8 @@ class Engine:
         self._stats_arena = None   # [slots, B, groups, 2] int64, zeroed once per network pass
         self._stats_next = 0
         self.attn_scratch_bytes = 4 << 30  # cap of the fp32 logits buffer of the batched spatial attention
+        # 1x1 shortcuts as extra K steps of conv2 (CVVAE_FUSE_SHORTCUT=0: separate launch + residual add, for A/B runs)
+        self.fuse_shortcut = os.environ.get("CVVAE_FUSE_SHORTCUT", "1") != "0"
 
     # ------------------------------------------------------------------ shape arithmetic
     def encoded_frames(self, T: int) -> int:
@@ -189,7 +192,8 @@ class Engine:
     def conv(self, a: Act, name: str, *, kernel, stride=(1, 1, 1), pads, pad_t, pad_hw, up_time=1,
              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
              weight_key: Optional[str] = None, ref_taps: Optional[int] = None,
-             stats: Optional[torch.Tensor] = None, want_stats: bool = False, k_alg: Optional[int] = None) -> Act:
+             stats: Optional[torch.Tensor] = None, want_stats: bool = False, k_alg: Optional[int] = None,
+             shortcut: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None) -> Act:
         """Convolution with the reference's padding expressed as ((t_lo,t_hi),(h_lo,h_hi),(w_lo,w_hi)).
 
         want_stats: also produce the consumer GroupNorm's (sum, sum^2) per (sample, group) in the epilogue
@@ -198,6 +202,8 @@ class Engine:
         wkey = weight_key or (name + ".weight")
         w = self.p[wkey]
         b = self.p.get(name + ".bias")
+        if shortcut is not None:   # (input [B,T,H,W,C2], matrix [Cout, C2], summed bias): fused as extra K steps
+            b = shortcut[2]
         B, T, H, W, _ = x.shape
         (tl, th), (hl, hh), (wl, wh) = pads
         kt, kh, kw = kernel
@@ -276,6 +282,8 @@ class Engine:
         else:
             if k_alg is not None:
                 skw["k_alg"] = k_alg
+            if shortcut is not None:
+                skw["sc_x"], skw["sc_w"] = shortcut[0], shortcut[1]
             self.ops.conv(x, w, b, kernel=kernel, stride=stride, offset=off, pad_t=pad_t, pad_hw=pad_hw,
                           up_time=up_time, residual=residual, out=out, ref_taps=ref_taps, **skw)
         return Act(out, stats=stats)
@@ -338,7 +346,16 @@ class Engine:
         # conv2 is a zero-padded per-frame 3x3 when half_3d, else another conv_cls 3x3x3
         h = self.gn(h, p + ".norm2", framed=(self.sd3 and not cfg.half_3d))
         sc_name = p + (".conv_shortcut" if self.sd3 else ".nin_shortcut")
+        conv2 = self.conv2 if cfg.half_3d else (lambda hh, nn, **kw: self.conv3(hh, nn, causal, **kw))
         if (sc_name + ".weight") in self.p:
+            if self.fuse_shortcut and self._tc_ok(a.t):
+                # K4: the 1x1 shortcut runs as extra K steps of conv2 on the block input (never written, never re-read,
+                # the sum rounded once); the two biases are pre-summed in fp32
+                key = p + ".conv2.bias+shortcut"
+                if key not in self.p:
+                    self.p[key] = (self.p[p + ".conv2.bias"] + self.p[sc_name + ".bias"]).contiguous()
+                wsc = self.p[sc_name + ".weight"]
+                return conv2(h, p + ".conv2", want_stats=True, shortcut=(a.t, wsc.view(wsc.shape[1], wsc.shape[2]), self.p[key]))
             shortcut = self.conv1(Act(a.t), sc_name).t
         else:
             shortcut = a.t
@@ -346,9 +363,7 @@ class Engine:
                 # residual operands share the (dense) output geometry
                 shortcut = self.ops.copy(shortcut, self.ops.empty(shortcut.shape, shortcut.dtype, shortcut.device))
         # every block output feeds a GroupNorm (next block's norm1 / norm_out) or a conv that ignores the sums
-        if cfg.half_3d:
-            return self.conv2(h, p + ".conv2", residual=shortcut, want_stats=True)
-        return self.conv3(h, p + ".conv2", causal, residual=shortcut, want_stats=True)
+        return conv2(h, p + ".conv2", residual=shortcut, want_stats=True)
 
     def spatial_attention(self, hn: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v_name: str) -> torch.Tensor:
         """softmax(q k^T / sqrt(C)) v per frame, one head (vae_models.py:446-461,500-528; diffusers Attention).

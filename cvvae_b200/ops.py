@@ -121,11 +121,13 @@ class CudaOps:
              out_f32: bool = False, bias_along_m: bool = False, w_ld: int = 0, cout: Optional[int] = None,
              force: Optional[str] = None, ref_taps: Optional[int] = None, gn_stats: Optional[torch.Tensor] = None,
              gn_groups: int = 32, w_per_batch: bool = False, x_shared: bool = False,
-             k_alg: Optional[int] = None) -> torch.Tensor:
+             k_alg: Optional[int] = None, sc_x: Optional[torch.Tensor] = None, sc_w: Optional[torch.Tensor] = None) -> torch.Tensor:
         """y = alpha * conv(x, w) + bias + residual.  ``w`` is packed [taps, Cout, Cin(ld)].
 
         Batched GEMM (attention): ``w_per_batch`` - w is [B, Cout, Cin(ld)], one matrix per batch item of y;
-        ``x_shared`` - x has batch 1 and is the left operand of every batch item."""
+        ``x_shared`` - x has batch 1 and is the left operand of every batch item.
+        Fused 1x1 shortcut: ``sc_x`` [B,T,H,W,C2] (the output's extents) times ``sc_w`` [Cout, C2] is accumulated into the
+        same fp32 accumulators as the taps (``bias`` then carries the sum of both biases)."""
         B, T, H, W, Ci = x.shape
         if x_shared:
             B = out.shape[0]
@@ -161,6 +163,11 @@ class CudaOps:
             d.gn_groups = gn_groups
         if residual is not None:
             assert residual.shape == out.shape and residual.stride() == out.stride(), "residual must share y's geometry"
+        if sc_w is not None:
+            assert sc_x is not None and tuple(sc_x.shape[:4]) == tuple(out.shape[:4]) and tuple(sc_w.shape) == (Co, sc_x.shape[4])
+            assert sc_w.is_contiguous() and sc_w.dtype == x.dtype
+            d.x2 = _t5(sc_x)
+            d.w2 = sc_w.data_ptr()
         fn = {None: self.lib.cvvae_conv3d, "tc": self.lib.cvvae_conv3d_tc, "direct": self.lib.cvvae_conv3d_direct}[force]
         if self.profile is None:
             L.check(fn(C.byref(d), _stream(x)), "cvvae_conv3d")
@@ -174,6 +181,11 @@ class CudaOps:
             mn, kt, kh, kw, ref_taps = 2 * B * t_conv * out.shape[2] * out.shape[3] * Co, k_alg, 1, 1, None
         self.profile["flops"][path] += mn * kt * kh * kw
         self.profile["ref_flops"][path] += mn * (ref_taps if ref_taps is not None else kt * kh * kw)
+        if sc_w is not None:   # the fused 1x1 shortcut's MACs (a separate conv in the reference) and its input bytes
+            sc = 2 * B * t_conv * out.shape[2] * out.shape[3] * Co * sc_x.shape[4]
+            self.profile["flops"][path] += sc
+            self.profile["ref_flops"][path] += sc
+            self.profile["bytes"][path] += sc_x.numel() * sc_x.element_size() + sc_w.numel() * sc_w.element_size()
         # algorithmic bytes: every operand once (input, weights, residual, output)
         self.profile["bytes"][path] += (x.numel() * x.element_size() + w.numel() * w.element_size() +
                                         out.numel() * out.element_size() * (2 if residual is not None else 1))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVVAE_ABI_VERSION 1
+#define CVVAE_ABI_VERSION 2
 
 enum { CVVAE_F16 = 0, CVVAE_BF16 = 1 };
 enum { CVVAE_PAD_ZERO = 0, CVVAE_PAD_REPLICATE = 1 };
@@ -93,6 +93,13 @@ typedef struct cvvae_conv_desc {
                                GroupNorm statistics of the consumer, produced in the conv epilogue instead of a
                                separate pass over y.  The caller zeroes it (several launches may add to it).  */
   int32_t gn_groups;
+  /* Optional fused 1x1 shortcut (ResnetBlock3D: `x = nin_shortcut(x); return x + h`, models/vae_models.py:386-388,406-410;
+   * conv_shortcut of the sd3 blocks): y += sum_ci x2[b,t,h,w,ci] * w2[co][ci], accumulated in the same fp32 accumulators
+   * as the taps (extra K steps), so the shortcut tensor is never written or re-read and the sum is rounded once.  x2 has
+   * the OUTPUT's [B,T,H,W] extents (stride-1 'same' convolutions only), channels-last, C % 8 == 0; w2 is [Cout][x2.C] in the
+   * activation dtype; `bias` then holds the sum of both biases.  w2 == NULL: none.  Tensor-core path only. */
+  cvvae_tensor5 x2;
+  const void* w2;
 } cvvae_conv_desc;
 
 /* Dispatcher: tcgen05 implicit-GEMM kernel when eligible (x.s_c==1, Cin%8==0, 16B-aligned strides,

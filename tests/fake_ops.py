@@ -46,7 +46,8 @@ class FakeOps:
 
     def conv(self, x, w, bias, *, kernel=(1, 1, 1), stride=(1, 1, 1), offset=(0, 0, 0), pad_t=PAD_ZERO, pad_hw=PAD_ZERO,
              up_time=1, residual=None, alpha=1.0, out=None, out_f32=False, bias_along_m=False, w_ld=0, cout=None,
-             force=None, ref_taps=None, gn_stats=None, gn_groups=32, w_per_batch=False, x_shared=False, k_alg=None):
+             force=None, ref_taps=None, gn_stats=None, gn_groups=32, w_per_batch=False, x_shared=False, k_alg=None,
+             sc_x=None, sc_w=None):
         self.launches += 1
         assert out is not None
         if w_per_batch or x_shared:
@@ -102,6 +103,8 @@ class FakeOps:
             c = Co // 2
             y = y.reshape(B, 2, c, To, Ho, Wo).permute(0, 2, 3, 1, 4, 5).reshape(B, c, 2 * To, Ho, Wo)[:, :, 1:]
         y = y.permute(0, 2, 3, 4, 1)  # logical [B,T,H,W,C]
+        if sc_w is not None:   # fused 1x1 shortcut: + sc_x @ sc_w^T, same accumulator (one rounding at the end)
+            y = y + torch.einsum("bthwc,oc->bthwo", sc_x.to(self.cd), sc_w.to(self.cd))
         if residual is not None:
             y = y + residual.to(self.cd)
         out.copy_(y.to(out.dtype))

@@ -124,6 +124,13 @@ CONV_CASES = {
     "pair_phase_up": ((1, 3, 70, 24, 128), 256, (3, 2, 2), (1, 1, 1), ((1, 1), (1, 0), (0, 1)), PAD_REPLICATE, PAD_ZERO, 2,
                       {"lattice_out": (0, 1)}),
     "pair_cout32": ((1, 2, 90, 20, 64), 32, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {}),
+    # fused 1x1 shortcut (K4): pair kernel (Cout 256 / 512), wide-slab persistent kernel (Cout 128), single-CTA kernel (Cout 64)
+    "sc_pair_n256": ((2, 2, 40, 40, 256), 256, (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {"shortcut": 128}),
+    "sc_pair_n512_333": ((1, 3, 36, 24, 128), 512, (3, 3, 3), (1, 1, 1), ((2, 0), (1, 1), (1, 1)), PAD_REPLICATE, PAD_ZERO, 1,
+                         {"shortcut": 256}),
+    "sc_wide_n128": ((2, 3, 70, 44, 128), 128, (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {"shortcut": 256}),
+    "sc_wide_n128_333": ((1, 3, 33, 21, 64), 128, (3, 3, 3), (1, 1, 1), ((1, 1), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {"shortcut": 72}),
+    "sc_single_n64": ((1, 2, 20, 28, 64), 64, (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), PAD_ZERO, PAD_ZERO, 1, {"shortcut": 32}),
     "conv1x1_spatial": ((1, 2, 20, 20, 128), 256, (1, 1, 1), (1, 1, 1), ((0, 0), (0, 0), (0, 0)), PAD_ZERO, PAD_ZERO, 1,
                         {"strided_in": True}),
 }
@@ -158,6 +165,10 @@ def _run_conv(ops, fake, case, dtype, force):
     residual = _rand(yshape, dtype, 6) if ex.get("residual") else None
     kw = dict(kernel=kernel, stride=stride, offset=(-tl, -hl, -wl), pad_t=pad_t, pad_hw=pad_hw, up_time=up_time,
               residual=residual, alpha=ex.get("alpha", 1.0))
+    if ex.get("shortcut"):
+        c2 = ex["shortcut"]
+        kw["sc_x"] = _rand(yshape[:4] + (c2,), dtype, 7)
+        kw["sc_w"] = _rand((Co, c2), dtype, 8, scale=c2 ** -0.5)
     got = ops.conv(x, w, bias, out=mk_out(), force=force, **kw)
     want = fake.conv(x, w, bias, out=torch.zeros(yshape, dtype=torch.float32, device=DEV),
                      **{**kw, "residual": residual})
@@ -283,7 +294,7 @@ def test_data_movement_is_bit_exact():
 
 
 @pytest.mark.parametrize("name", ["causal333", "frame133_odd", "uptime", "wide512", "res_bias_alpha", "phase322", "cin32",
-                                  "pair_n128", "pair_n256_odd", "pair_phase_up"])
+                                  "pair_n128", "pair_n256_odd", "pair_phase_up", "sc_pair_n256", "sc_wide_n128"])
 def test_conv_fused_groupnorm_stats(name):
     """The conv epilogue's (sum, sum^2) per (sample, group) equal those of the tensor it stored."""
     ops, fake = _ops(), FakeOps()
@@ -301,8 +312,11 @@ def test_conv_fused_groupnorm_stats(name):
     Wo = (W + wl + wh - kernel[2]) // stride[2] + 1
     yshape = (B, 2 * To - 1, Ho, Wo, yC) if up_time == 2 else (B, To, Ho, Wo, Co)
     y = torch.zeros(yshape, dtype=torch.float16, device=DEV)
+    skw = {}
+    if ex.get("shortcut"):
+        skw = dict(sc_x=_rand(yshape[:4] + (ex["shortcut"],), torch.float16, 7), sc_w=_rand((Co, ex["shortcut"]), torch.float16, 8, scale=0.1))
     ops.conv(x, w, bias, kernel=kernel, stride=stride, offset=(-tl, -hl, -wl), pad_t=pad_t, pad_hw=pad_hw, up_time=up_time,
-             out=y, gn_stats=stats, gn_groups=32)
+             out=y, gn_stats=stats, gn_groups=32, **skw)
     torch.cuda.synchronize()
     v = y.double().reshape(B, -1, 32, yC // 32)
     want = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
@@ -554,3 +568,27 @@ def test_groupnorm_fixed_point_statistics_at_large_magnitudes():
     want_s = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
     got_s = torch.stack([st[..., 0].double() / 2.0 ** 20, st[..., 1].double() / 2.0 ** 18], dim=-1)
     torch.testing.assert_close(got_s, want_s, rtol=1e-5, atol=1.0)
+
+
+def test_fused_shortcut_bf16_and_engine_equivalence():
+    """K4 in bf16, and the engine's fused ResnetBlock (shortcut as extra K steps of conv2) against its own unfused form
+    (separate 1x1 launch + residual add): same math up to one rounding of the shortcut tensor."""
+    ops, fake = _ops(), FakeOps()
+    got, want = _run_conv(ops, fake, CONV_CASES["sc_wide_n128"], torch.bfloat16, "tc")
+    torch.testing.assert_close(got.float(), want, **_tol(torch.bfloat16))
+    from cvvae_b200 import CVVAEModel
+    from oracle import cvvae_oracle as O
+    wrap = dict(tile_spatial_size=None, en_de_n_frames_a_time=None)
+    m = CVVAEModel(ch=64, **wrap)
+    m.load_state_dict(O.make_state_dict(O.VAEConfig(variant="sd21", ch=64, **wrap), 1234))
+    m = m.half().cuda()
+    x = O.synthetic_video((1, 3, 5, 64, 48), 3).half().cuda()
+    fused = m.encode(x).latent_dist.parameters.float()
+    n_fused = ops.launch_count()
+    rec_f = m.decode(fused[:, :4].half()).sample.float()
+    m._engine().fuse_shortcut = False
+    plain = m.encode(x).latent_dist.parameters.float()
+    rec_p = m.decode(plain[:, :4].half()).sample.float()
+    assert not torch.equal(fused, plain)                      # different roundings: really two code paths
+    assert (fused - plain).abs().max().item() < 2e-2 and (rec_f - rec_p).abs().max().item() < 5e-2
+    assert (fused - plain).abs().mean().item() < 1e-3
