@@ -1488,10 +1488,6 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
                     "conv: a fused shortcut needs a stride-1 spatial convolution without residual / interleave");
     CVVAE_CHECK_ARG(-d->off_h >= 0 && -d->off_h < d->KH && -d->off_w >= 0 && -d->off_w < d->KW && d->off_t <= 0 && -d->off_t < d->KT,
                     "conv: fused shortcut needs the centre tap inside the kernel window");
-    if (persist_want && !p.wide) {
-      set_error("conv_tc: fused shortcut unsupported on the non-wide persistent path");
-      return CVVAE_E_UNSUPPORTED;
-    }
     p.Cin2 = x2.C;
     p.cblocks2 = (x2.C + 63) / 64;
     if (p.wide) p.sc_off16 = static_cast<uint32_t>((-d->off_h) * p.PW + (-d->off_w)) * 8u;
@@ -1558,8 +1554,9 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   }
 
   CVVAE_CHECK_ARG(!p.wide || p.persist, "conv_tc: internal: wide-slab plan without the persistent kernel");
-  if (p.cblocks2 && p.swap && !p.persist) {
-    set_error("conv_tc: fused shortcut unsupported on the non-persistent operand-swapped path");
+  if (p.cblocks2 && ((p.swap && !p.persist) || (p.persist && !p.wide))) {
+    // (neither arises with the default knobs: stride-1 spatial kernels with Cout == 128 take the wide persistent path)
+    set_error("conv_tc: fused shortcut unsupported on the operand-swapped paths without wide slabs");
     return CVVAE_E_UNSUPPORTED;
   }
   const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_hp * p.B * CG;
