@@ -36,7 +36,8 @@ struct ConvTcParams {
   // tiling
   int TW, ROWS, NACC, TH, N_cta, KHs, n_hgroups, slab_rows;
   int tiles_w, tiles_h, n_tiles_n, cblocks, flat;
-  int tiles_hp;  // h-tiles per grid column: tiles_h, or ceil(tiles_h / 2) CTA pairs with cta_group::2
+  int tiles_hg, tiles_wg;  // grid extents in tiles: a CTA pair (cta_group::2) owns two tiles adjacent in H (default) or, with
+  int pair_w;              // wide slabs, in W (pair_w = 1); tiles_hg / tiles_wg = ceil(tiles / 2) along the paired axis
   int NA, NB;
   uint32_t slab_bytes, b_bytes, idesc;
   // epilogue
@@ -81,10 +82,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int rank
   id /= p.n_tiles_n;
   c.t = id % p.T_out;
   id /= p.T_out;
-  c.w0 = (id % p.tiles_w) * (p.flat ? p.NACC * 128 : p.TW);
-  id /= p.tiles_w;
-  c.h0 = ((id % p.tiles_hp) * CG + rank) * p.TH;  // the two CTAs of a pair own vertically adjacent tiles
-  c.b = id / p.tiles_hp;
+  const int cgw = p.pair_w ? CG : 1, cgh = p.pair_w ? 1 : CG;   // the two CTAs of a pair own tiles adjacent in W or in H
+  c.w0 = ((id % p.tiles_wg) * cgw + (p.pair_w ? rank : 0)) * (p.flat ? p.NACC * 128 : p.TW);
+  id /= p.tiles_wg;
+  c.h0 = ((id % p.tiles_hg) * cgh + (p.pair_w ? 0 : rank)) * p.TH;
+  c.b = id / p.tiles_hg;
   return c;
 }
 
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + static_cast<size_t>(p.NA) * p.slab_bytes;
+  uint8_t* sB = sA + static_cast<size_t>(p.NA) * p.slab_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(p.NB) * p.b_bytes);
   uint64_t* fullA = bars;         // [8]
   uint64_t* emptyA = bars + 8;    // [8]
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {
     int rem = p.H_out - tc.h0;
     nacc_eff = max(0, min(p.NACC, (rem + p.ROWS - 1) / p.ROWS));
+    if (tc.w0 >= p.W_out) nacc_eff = 0;   // idle half of an odd last pair along W
   }
 
   if (threadIdx.x < 128) gn_bins[threadIdx.x] = 0ull;
@@ -197,9 +200,32 @@ __global__ void __launch_bounds__(kThreads, 1)
       int slot = 0;
       uint32_t phase = 0;
       const int xb = (p.flags & CVVAE_CONV_X_SHARED) ? 0 : tc.b;  // batched GEMM with one shared left operand
+      auto load_slab = [&](const CUtensorMap* tm, int c0, int cw, int chh, int ti) {
+        wait_bar(&emptyA[slot], phase ^ 1);
+        uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_stride;
+        if (ptx::elect_one()) {
+          if (CG == 2) {
+            if (rank == 0) ptx::mbar_expect_tx(&fullA[slot], 2u * p.slab_bytes);   // both CTAs' bytes land on the leader's barrier
+            ptx::tma_load_5d_cg2(dst, tm, ptx::mapa_u32(ptx::smem_u32(&fullA[slot]), 0), c0, cw, chh, ti, xb);
+          } else {
+            ptx::mbar_expect_tx(&fullA[slot], p.slab_bytes);
+            ptx::tma_load_5d(dst, tm, &fullA[slot], c0, cw, chh, ti, xb);
+          }
+        }
+        __syncwarp();
+        if (++slot == p.NA) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      if (p.wide) {
+        // one slab per (kt, channel block) for all KH x KW taps (8-wide tiles, see conv_tc_psw_kernel)
+        for_each_wslab(p, tc.t, [&](int kt, int ti, int cb) { load_slab(&tmA, cb * 64, tc.w0 + p.off_w, tc.h0 + p.off_h, ti); });
+        for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) load_slab(&tmA2, cb2 * 64, tc.w0 + p.off_w, tc.h0 + p.off_h, tc.t);
+      } else {
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&emptyA[slot], phase ^ 1);
-        uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_bytes;
+        uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_stride;
         if (ptx::elect_one()) {
           if (p.flat) {
             ptx::mbar_expect_tx(&fullA[slot], static_cast<uint32_t>(nacc_eff) * 128u * 128u);
@@ -225,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // fused 1x1 shortcut: the (unshifted) window of the second input, one slab per 64-channel block
       for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {
         wait_bar(&emptyA[slot], phase ^ 1);
-        uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_bytes;
+        uint8_t* dst = sA + static_cast<size_t>(slot) * p.slab_stride;
         if (ptx::elect_one()) {
           if (CG == 2) {
             if (rank == 0) ptx::mbar_expect_tx(&fullA[slot], 2u * p.slab_bytes);
@@ -241,12 +267,38 @@ __global__ void __launch_bounds__(kThreads, 1)
           phase ^= 1;
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- B producer
     {
       int slot = 0;
       uint32_t phase = 0;
+      if (p.wide) {
+        auto load_w = [&](const CUtensorMap* tm, int c0, int tap) {
+          wait_bar(&emptyB[slot], phase ^ 1);
+          if (ptx::elect_one()) {
+            if (CG == 2) {
+              if (rank == 0) ptx::mbar_expect_tx(&fullB[slot], 2u * p.b_bytes);
+              ptx::tma_load_3d_cg2(sB + static_cast<size_t>(slot) * p.b_bytes, tm, ptx::mapa_u32(ptx::smem_u32(&fullB[slot]), 0), c0,
+                                   tc.n0 + rank * (p.N_cta / 2), tap);
+            } else {
+              ptx::mbar_expect_tx(&fullB[slot], p.b_bytes);
+              ptx::tma_load_3d(sB + static_cast<size_t>(slot) * p.b_bytes, tm, &fullB[slot], c0, tc.n0, tap);
+            }
+          }
+          __syncwarp();
+          if (++slot == p.NB) {
+            slot = 0;
+            phase ^= 1;
+          }
+        };
+        for_each_wslab(p, tc.t, [&](int kt, int ti, int cb) {
+          for (int kh = 0; kh < p.KH; ++kh)
+            for (int kw = 0; kw < p.KW; ++kw) load_w(&tmB, cb * 64, (kt * p.KH + kh) * p.KW + kw);
+        });
+        for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) load_w(&tmB2, cb2 * 64, 0);
+      } else {
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         for (int khs = 0; khs < p.KHs; ++khs) {
           // batched GEMM: the "tap" axis of the weight tensor indexes the batch item (1x1x1 problems only)
@@ -288,6 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           phase ^= 1;
         }
       }
+      }
     }
   } else if (warp == 2 && rank == 0) {
     // ------------------------------------------------------------- MMA issuer (the pair's leader when CG = 2)
@@ -307,13 +360,58 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
       constexpr uint32_t kDescLoFlags = 1u << 16;  // LBO field (canonical 1 for swizzled K-major)
       bool first = true;
+      if (p.wide) {
+        // positions (A) operand: 16 groups of 8 rows per 128-row sub-tile, one group per image row of the 8-wide tile, PW * 128 B
+        // apart; tap (kh, kw) and sub-tile s are start-address offsets ((kh + s * ROWS) * PW + kw) * 128 B into the one slab
+        const uint32_t descHiA = static_cast<uint32_t>(p.PW * 8) | (1u << 14) | (2u << 29);
+        auto mma_slab = [&](int ch_total, int cb, uint32_t off16_base, int n_taps_h, int n_taps_w) {
+          wait_bar(&fullA[slotA], phaseA);
+          const int ch_left = ch_total - cb * 64;
+          const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
+          const uint32_t a_lo0 = (((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_stride) >> 4) & 0x3FFFu) | kDescLoFlags) + off16_base;
+          for (int kh = 0; kh < n_taps_h; ++kh) {
+            for (int kw = 0; kw < n_taps_w; ++kw) {
+              wait_bar(&fullB[slotB], phaseB);
+              ptx::tc_fence_after();
+              const uint32_t b_lo0 = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+              if (ptx::elect_one()) {
+                for (int s = 0; s < nacc_eff; ++s) {
+                  const uint32_t a_lo = a_lo0 + static_cast<uint32_t>((kh + s * p.ROWS) * p.PW + kw) * 8u;
+                  const uint32_t d = tmem_base + static_cast<uint32_t>(s) * ncta;
+                  for (int k = 0; k < ksteps; ++k) {
+                    if (CG == 2) ptx::umma_f16_lohi2_cg2(d, a_lo + 2 * k, descHiA, b_lo0 + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+                    else ptx::umma_f16_lohi2(d, a_lo + 2 * k, descHiA, b_lo0 + 2 * k, kDescHi, idesc, accumulate | static_cast<uint32_t>(k));
+                  }
+                }
+                if (CG == 2) ptx::umma_commit_pair(&emptyB[slotB]); else ptx::umma_commit(&emptyB[slotB]);
+              }
+              __syncwarp();
+              accumulate = 1;
+              if (++slotB == p.NB) {
+                slotB = 0;
+                phaseB ^= 1;
+              }
+            }
+          }
+          if (ptx::elect_one()) {
+            if (CG == 2) ptx::umma_commit_pair(&emptyA[slotA]); else ptx::umma_commit(&emptyA[slotA]);
+          }
+          __syncwarp();
+          if (++slotA == p.NA) {
+            slotA = 0;
+            phaseA ^= 1;
+          }
+        };
+        for_each_wslab(p, tc.t, [&](int kt, int ti, int cb) { mma_slab(p.Cin, cb, 0u, p.KH, p.KW); });
+        for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) mma_slab(p.Cin2, cb2, p.sc_off16, 1, 1);   // fused shortcut: the centre tap
+      } else {
       for_each_slab(p, tc.t, [&](int kt, int ti, int hg, int kw, int cb) {
         wait_bar(&fullA[slotA], phaseA);
         if (traced && first && lane == 0) trc[2] = ptx::globaltimer_ns();
         // K = 16 per MMA; channels beyond Cin are TMA zero-fill in both operands, skip those MMAs entirely
         const int ch_left = p.Cin - cb * 64;
         const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
-        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_stride) >> 4) & 0x3FFFu) | kDescLoFlags;
         for (int khs = 0; khs < p.KHs; ++khs) {
           wait_bar(&fullB[slotB], phaseB);
           ptx::tc_fence_after();
@@ -375,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_after();
         const int ch_left = p.Cin2 - cb2 * 64;
         const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
-        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
+        const uint32_t a_lo0 = ((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_stride) >> 4) & 0x3FFFu) | kDescLoFlags;
         const uint32_t b_lo0 = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
         if (ptx::elect_one()) {
           for (int s = 0; s < nacc_eff; ++s) {
@@ -404,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           slotA = 0;
           phaseA ^= 1;
         }
+      }
       }
       if (ptx::elect_one()) {
         if (CG == 2) ptx::umma_commit_pair(accFull); else ptx::umma_commit(accFull);
@@ -1232,7 +1331,7 @@ static bool encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64
 
 // Experiment knobs (environment), read ONCE per process - nothing on the launch path calls getenv.
 struct Knobs {
-  int nacc, persist, fill, cta_group, tw, na, swap, wide, pw, smem_reserve;
+  int nacc, persist, fill, cta_group, tw, na, swap, wide, wide2, pw, smem_reserve;
   static int env(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -1240,7 +1339,8 @@ struct Knobs {
   Knobs()
       : nacc(env("CVVAE_CONV_NACC", 0)), persist(env("CVVAE_CONV_PERSIST", 1)), fill(env("CVVAE_CONV_FILL", 1)),
         cta_group(env("CVVAE_CONV_CTA_GROUP", 0)), tw(env("CVVAE_CONV_TW", 0)), na(env("CVVAE_CONV_NA", 0)),
-        swap(env("CVVAE_CONV_SWAP", 1)), wide(env("CVVAE_CONV_WIDE", 1)), pw(env("CVVAE_CONV_PW", 0)),
+        swap(env("CVVAE_CONV_SWAP", 1)), wide(env("CVVAE_CONV_WIDE", 1)), wide2(env("CVVAE_CONV_WIDE2", 1)),
+        pw(env("CVVAE_CONV_PW", 0)),
         smem_reserve(env("CVVAE_CONV_SMEM_RESERVE", 0)) {}
 };
 static const Knobs& knobs() {
@@ -1349,6 +1449,10 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   // wide slabs (one slab per (kt, channel block) for all KH x KW taps): stride-1 spatial kernels of the persistent path
   const bool wide_want = persist_want && kn.wide && kn.swap && kn.cta_group != 2 && kn.nacc == 0 && d->sh == 1 && d->sw == 1 &&
                          d->KW > 1 && d->KW <= 3 && d->KH <= 3;
+  // ... and of the Cout >= 256 layers (non-persistent kernel, CTA pairs side by side along W)
+  const bool wide2_want = !persist_want && kn.wide2 && N_cta == 256 && kn.nacc == 0 && kn.tw == 0 && d->sh == 1 && d->sw == 1 &&
+                          d->KW > 1 && d->KW <= 3 && d->KH <= 3 && !flat_shape;
+  const bool wide_any = wide_want || wide2_want;
   p.flat = (p.H_out == 1 && d->KH == 1 && d->KW == 1 && d->sw == 1 && d->sh == 1 && x.H == 1) ? 1 : 0;
   if (d->flags & (CVVAE_CONV_W_PER_BATCH | CVVAE_CONV_X_SHARED))
     CVVAE_CHECK_ARG(p.flat, "conv: batched-GEMM flags need a flat problem (H == 1, 1x1x1, stride 1)");
@@ -1389,7 +1493,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     if (tw_env >= 8 && tw_env <= 128 && (tw_env & (tw_env - 1)) == 0 && tw_env * d->sw <= 256 &&
         ((128 / tw_env) * p.NACC + p.KHs - 1) * d->sh <= 256)
       best_tw = tw_env;
-    if (wide_want) best_tw = 8;   // one 8-row swizzle group per image row of the tile
+    if (wide_any) best_tw = 8;   // one 8-row swizzle group per image row of the tile
     p.TW = best_tw;
     p.ROWS = 128 / p.TW;
     p.TH = p.ROWS * p.NACC;
@@ -1406,7 +1510,7 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   p.slab_bytes = p.flat ? static_cast<uint32_t>(p.NACC) * 16384u : static_cast<uint32_t>(p.slab_rows * p.TW) * 128u;
   p.wide = 0;
   p.PW = p.TW;
-  if (wide_want && !p.flat) {
+  if (wide_any && !p.flat) {
     p.wide = 1;
     p.PW = 8 + d->KW - 1;
     if (kn.pw > p.PW && kn.pw <= 32) p.PW = kn.pw;   // experiment knob: slab pitch in positions
@@ -1418,9 +1522,11 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
   // measured (tools/bench_conv.py): pairs help the N_cta = 256 layers (half the weight bytes per CTA, up to +10 %)
   // and cost 0-16 % on the N_cta = 128 layers, so they are on for N_cta = 256 only (CVVAE_CONV_CTA_GROUP=2 forces them
   // wherever possible, =1 switches them off)
-  const bool pair_ok = !p.flat && p.tiles_h >= 2 && N_cta >= 32;
+  p.pair_w = (p.wide && !persist_want) ? 1 : 0;   // wide slabs: 8-wide tiles, pair them along W (always plenty, never odd rows)
+  const bool pair_ok = !p.flat && (p.pair_w ? p.tiles_w >= 2 : p.tiles_h >= 2) && N_cta >= 32;
   const int CG = (cg_env == 1 || !pair_ok) ? 1 : ((cg_env == 2 || N_cta == 256) ? 2 : 1);
-  p.tiles_hp = (p.tiles_h + CG - 1) / CG;
+  p.tiles_hg = p.pair_w ? p.tiles_h : (p.tiles_h + CG - 1) / CG;
+  p.tiles_wg = p.pair_w ? (p.tiles_w + CG - 1) / CG : p.tiles_w;
   p.b_bytes = static_cast<uint32_t>(N_cta / CG) * 128u;  // weight rows staged per CTA
   p.idesc = ptx::umma_idesc_f16(d->dtype == CVVAE_BF16 ? 1 : 0, 128 * CG, N_cta);
 
@@ -1553,13 +1659,13 @@ int conv_tc_launch(const cvvae_conv_desc* d, cudaStream_t stream) {
     p.gn_cpg = cpg;
   }
 
-  CVVAE_CHECK_ARG(!p.wide || p.persist, "conv_tc: internal: wide-slab plan without the persistent kernel");
+  CVVAE_CHECK_ARG(!wide_want || !p.wide || p.persist, "conv_tc: internal: wide-slab plan without the persistent kernel");
   if (p.cblocks2 && ((p.swap && !p.persist) || (p.persist && !p.wide))) {
     // (neither arises with the default knobs: stride-1 spatial kernels with Cout == 128 take the wide persistent path)
     set_error("conv_tc: fused shortcut unsupported on the operand-swapped paths without wide slabs");
     return CVVAE_E_UNSUPPORTED;
   }
-  const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_w * p.tiles_hp * p.B * CG;
+  const long long grid = 1ll * p.n_tiles_n * p.T_out * p.tiles_wg * p.tiles_hg * p.B * CG;
   CVVAE_CHECK_ARG(grid > 0 && grid < (1ll << 31), "conv_tc: grid size %lld out of range", grid);
   CVVAE_DISPATCH_DTYPE(d->dtype, {
     static PerDeviceOnce attr_set;   // the > 48 KB shared-memory opt-in is per device
