@@ -162,4 +162,6 @@ def test_full_size_parity_against_reference_algorithm(variant, dtype, shape):
                        reference16_vs_fp32=dict(moments=r_m, recon=r_r), pass_fraction_rtol1e_3_atol1e_4=pf), f, indent=1)
     for mine, ref in ((mine_m, r_m), (mine_r, r_r)):
         assert mine[1] <= ref[1] and mine[2] <= ref[2] and mine[0] <= 1.25 * ref[0], (mine, ref)
-    assert pf["engine_moments"] >= pf["reference16_moments"] and pf["engine_recon"] >= pf["reference16_recon"], pf
+    for key, n in (("moments", gold_m.numel()), ("recon", gold_r.numel())):
+        ref_pf = pf["reference16_" + key]
+        assert pf["engine_" + key] >= ref_pf - 2.0 * (ref_pf * (1.0 - ref_pf) / n) ** 0.5, (key, pf)
