@@ -93,13 +93,20 @@ def peaks():
     return 1400.0, "fallback 1.4 PFLOP/s sustained (of fallback)"
 
 
-def source_hash():
-    """sha256 over the CUDA sources + the C header: identifies the kernels a committed ncu capture belongs to."""
+def source_hash(root=None):
+    """sha256 over the CUDA sources + the C header with comments and whitespace removed: identifies the KERNELS a
+    committed ncu capture belongs to (editing a comment does not make a capture stale, editing code does)."""
+    import re
+    root = root or ROOT
     h = hashlib.sha256()
-    d = os.path.join(ROOT, "cvvae_b200", "csrc")
+    d = os.path.join(root, "cvvae_b200", "csrc")
     for f in sorted(os.listdir(d)) + ["../../include/cvvae_b200.h"]:
-        with open(os.path.join(d, f), "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+        with open(os.path.join(d, f), "r", encoding="utf-8", errors="replace") as fh:
+            src = fh.read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)     # block comments
+        src = re.sub(r"//[^\n]*", "", src)                  # line comments (no '//' occurs inside string literals here)
+        src = re.sub(r"\s+", "", src)
+        h.update(f.encode() + b"\0" + src.encode())
     return h.hexdigest()[:16]
 
 

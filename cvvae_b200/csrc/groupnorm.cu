@@ -1,6 +1,6 @@
 // GroupNorm(32) statistics + fused normalise/affine/SiLU, and the token LayerNorm of the temporal
-// attention.  HBM-bound kernels: 128-bit loads/stores, grids sized in multiples of the SM count,
-// statistics reduced thread -> block (shared fp64 atomics) -> device (global fp64 atomics).
+// attention.  HBM-bound kernels: 128-bit loads/stores, ~8 CTAs per SM, statistics reduced thread (fp32) -> block
+// (shared 64-bit fixed-point atomics) -> device (global 64-bit fixed-point atomics; order-independent, reproducible).
 //
 // Replaces Normalize()+nonlinearity (reference models/vae_models.py:187-195,392-401), nn.GroupNorm+nn.SiLU
 // of models/vae_blocks3d_sd3.py, and norm_t (models/vae_models.py:571).  One rounding to 16 bit at the

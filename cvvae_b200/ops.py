@@ -157,7 +157,7 @@ class CudaOps:
         d.flags = ((L.CONV_BIAS_ALONG_M if bias_along_m else 0) | (L.CONV_OUT_F32 if out_f32 else 0) |
                    (L.CONV_W_PER_BATCH if w_per_batch else 0) | (L.CONV_X_SHARED if x_shared else 0))
         d.alpha = alpha
-        if gn_stats is not None:  # fp64 [B, groups, 2], zeroed by the caller; the epilogue accumulates into it
+        if gn_stats is not None:  # int64 fixed point [B, groups, 2], zeroed by the caller; the epilogue accumulates into it
             assert gn_stats.dtype == torch.int64 and gn_stats.is_contiguous()
             d.gn_stats = gn_stats.data_ptr()
             d.gn_groups = gn_groups

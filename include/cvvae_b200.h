@@ -14,8 +14,8 @@
  *   - every call is asynchronous on the `stream` it is given (a cudaStream_t passed as void*).
  *   - activations are channels-last: element (b,t,h,w,c) lives at b*s_b + t*s_t + h*s_h + w*s_w + c*s_c
  *     (strides in ELEMENTS).  The tensor-core path needs s_c == 1 on its input.
- *   - dtype: CVVAE_F16 or CVVAE_BF16 for activations and packed weights; bias / norm parameters /
- *     statistics are fp32 (statistics accumulators fp64).
+ *   - dtype: CVVAE_F16 or CVVAE_BF16 for activations and packed weights; bias / norm parameters are fp32;
+ *     GroupNorm statistics are 64-bit fixed point (order-independent integer accumulation, see below).
  */
 #ifndef CVVAE_B200_H_
 #define CVVAE_B200_H_
