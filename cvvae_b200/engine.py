@@ -131,7 +131,8 @@ class Engine:
         self._stats_next = 0
         self.attn_scratch_bytes = 4 << 30  # cap of the fp32 logits buffer of the batched spatial attention
         # 1x1 shortcuts as extra K steps of conv2 (CVVAE_FUSE_SHORTCUT=0: separate launch + residual add, for A/B runs)
-        self.fuse_shortcut = os.environ.get("CVVAE_FUSE_SHORTCUT", "1") != "0"
+        # (the experiment knob CVVAE_CONV_WIDE=0 selects a persistent-kernel variant without the shortcut K steps)
+        self.fuse_shortcut = os.environ.get("CVVAE_FUSE_SHORTCUT", "1") != "0" and os.environ.get("CVVAE_CONV_WIDE", "1") != "0"
 
     # ------------------------------------------------------------------ shape arithmetic
     def encoded_frames(self, T: int) -> int:
