@@ -448,16 +448,7 @@ class Engine:
                 name = f"{E}down_blocks.{lvl}.resnets.{b}" if self.sd3 else f"{E}down.{lvl}.block.{b}"
                 h = self.resblock(h, name, causal)
             if lvl != L - 1:
-                st = 2 if lvl % 2 == 0 else 1
-                if self.sd3:
-                    # Downsample3D -> conv_cls(k3, stride, padding=1): vae_blocks3d_sd3.py:200-210
-                    tp = (2, 0) if causal else (1, 1)
-                    h = self.conv(h, f"{E}down_blocks.{lvl}.downsamplers.0.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
-                                  pads=(tp, (1, 1), (1, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_REPLICATE, want_stats=True)
-                else:
-                    # Downsample3D.forward vae_models.py:251-263: zero pad right/bottom, replicate 2 frames in front
-                    h = self.conv(h, f"{E}down.{lvl}.downsample.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
-                                  pads=((2, 0), (0, 1), (0, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_ZERO, want_stats=True)
+                h = self.downsample(h, lvl, causal)
         if self.sd3:
             h = self.resblock(h, E + "mid_block.resnets.0", causal)
             if cfg.mid_block_add_attention:
@@ -520,6 +511,18 @@ class Engine:
         else:
             self.conv3(h, D + "conv_out", causal, out=out.permute(0, 2, 3, 4, 1))
         return out
+
+    def downsample(self, h: Act, lvl: int, causal: bool) -> Act:
+        """Downsample3D.forward of encoder level `lvl` (time stride 2 at the even levels)."""
+        st = 2 if lvl % 2 == 0 else 1
+        if self.sd3:
+            # Downsample3D -> conv_cls(k3, stride, padding=1): vae_blocks3d_sd3.py:200-210
+            tp = (2, 0) if causal else (1, 1)
+            return self.conv(h, f"encoder.down_blocks.{lvl}.downsamplers.0.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
+                             pads=(tp, (1, 1), (1, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_REPLICATE, want_stats=True)
+        # Downsample3D.forward vae_models.py:251-263: zero pad right/bottom, replicate 2 frames in front
+        return self.conv(h, f"encoder.down.{lvl}.downsample.conv", kernel=(3, 3, 3), stride=(st, 2, 2),
+                         pads=((2, 0), (0, 1), (0, 1)), pad_t=PAD_REPLICATE, pad_hw=PAD_ZERO, want_stats=True)
 
     def upsample(self, a: Act, name: str, up_time: int, causal: bool) -> Act:
         """Upsample3D.forward (vae_models.py:214-235, vae_blocks3d_sd3.py:314-364): nearest x(1,2,2), 3x3x3 conv
