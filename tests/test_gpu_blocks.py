@@ -26,5 +26,5 @@ def test_block_matches_reference_block_fp16(name):
     allrec = json.load(open(path)) if os.path.exists(path) else {}
     allrec[name] = rec
     json.dump(allrec, open(path, "w"), indent=1)
-    # a few fp16 roundings of O(1) activations: mean error ~1e-3 of the mean magnitude, max a few 1e-2
-    assert rec["mean_abs_err"] <= 3e-3 * max(scale, 1.0) and rec["max_abs_err"] <= 5e-2 * max(scale, 1.0), rec
+    # a few fp16 roundings of O(1) activations; measured (profiles/r02_block_parity.csv): mean 1.6e-4 .. 2.7e-4, max 1.0e-3 .. 3.3e-3
+    assert rec["mean_abs_err"] <= 6e-4 * max(scale, 1.0) and rec["max_abs_err"] <= 1e-2 * max(scale, 1.0), rec
