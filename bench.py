@@ -184,7 +184,7 @@ def usable_cores():
 
 def sample_shape(n_runs):
     """Bounded CPU sample per step, shrunk when many runs are asked for so that the arm ends within a few minutes."""
-    side = 192 if n_runs <= 6 else (128 if n_runs <= 26 else 96)
+    side = 192 if n_runs <= 6 else (128 if n_runs <= 30 else 96)
     return (1, 3, 17, side, side)
 
 
