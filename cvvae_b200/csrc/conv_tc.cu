@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t descHiA = static_cast<uint32_t>(p.PW * 8) | (1u << 14) | (2u << 29);
         auto mma_slab = [&](int ch_total, int cb, uint32_t off16_base, int n_taps_h, int n_taps_w) {
           wait_bar(&fullA[slotA], phaseA);
+          if (traced && first && lane == 0) trc[2] = ptx::globaltimer_ns();
           const int ch_left = ch_total - cb * 64;
           const int ksteps = ch_left >= 64 ? 4 : (ch_left + 15) >> 4;
           const uint32_t a_lo0 = (((ptx::smem_u32(sA + static_cast<size_t>(slotA) * p.slab_stride) >> 4) & 0x3FFFu) | kDescLoFlags) + off16_base;
@@ -373,6 +374,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int kw = 0; kw < n_taps_w; ++kw) {
               wait_bar(&fullB[slotB], phaseB);
               ptx::tc_fence_after();
+              if (traced && first && lane == 0) trc[3] = ptx::globaltimer_ns();
+              first = false;
               const uint32_t b_lo0 = ((ptx::smem_u32(sB + static_cast<size_t>(slotB) * p.b_bytes) >> 4) & 0x3FFFu) | kDescLoFlags;
               if (ptx::elect_one()) {
                 for (int s = 0; s < nacc_eff; ++s) {
